@@ -1,0 +1,126 @@
+// gl.cuh -- Goldilocks field (p = 2^64 - 2^32 + 1) and its quadratic extension F_p[u]/(u^2 - 7) on the device.
+//
+// Replaces, for the GPU path, `boojum::field::goldilocks::{GoldilocksField, GoldilocksExt2}` as used by the
+// reference's prover call (/root/reference/src/prover_utils.rs:12,16,36-44).  All values are kept CANONICAL
+// (< p) at function boundaries so results are bit-identical to the CPU oracle (oracle/gl64.h).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#define GL_P 0xFFFFFFFF00000001ULL
+#define GL_EPS 0xFFFFFFFFULL
+#define GL_ROOT_2_32 0x185629dcda58878cULL
+#define GL_GEN 7ULL
+
+#ifdef __CUDACC__
+#define GL_HD __host__ __device__ __forceinline__
+#else
+#define GL_HD inline
+#endif
+
+namespace gl {
+
+GL_HD uint64_t canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+
+GL_HD uint64_t add(uint64_t a, uint64_t b) {
+    uint64_t s = a + b;
+    // a, b < p: either the 64-bit add wrapped (true sum >= 2^64 > p) or s may be in [p, 2^64)
+    if (s < a || s >= GL_P) s -= GL_P;
+    return s;
+}
+GL_HD uint64_t sub(uint64_t a, uint64_t b) {
+    uint64_t d = a - b;
+    if (a < b) d += GL_P;
+    return d;
+}
+GL_HD uint64_t neg(uint64_t a) { return a ? GL_P - a : 0; }
+GL_HD uint64_t dbl(uint64_t a) { return add(a, a); }
+
+// 128-bit -> canonical.  2^64 = 2^32 - 1 and 2^96 = -1 (mod p)
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+    uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+    uint64_t t0 = lo - hh;
+    if (lo < hh) t0 -= GL_EPS;       // + p (mod 2^64)
+    uint64_t t1 = (hl << 32) - hl;   // hl * (2^32 - 1)
+    uint64_t r = t0 + t1;
+    if (r < t0) r += GL_EPS;         // wrapped: - p (mod 2^64) -- cannot wrap twice
+    return canon(r);
+}
+
+GL_HD uint64_t mul(uint64_t a, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return reduce128(a * b, __umul64hi(a, b));
+#else
+    unsigned __int128 x = (unsigned __int128)a * b;
+    return reduce128((uint64_t)x, (uint64_t)(x >> 64));
+#endif
+}
+GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
+
+GL_HD uint64_t pow(uint64_t b, uint64_t e) {
+    uint64_t r = 1;
+    while (e) {
+        if (e & 1) r = mul(r, b);
+        b = sqr(b);
+        e >>= 1;
+    }
+    return r;
+}
+GL_HD uint64_t inv(uint64_t a) { return pow(a, GL_P - 2); }
+GL_HD uint64_t omega(int log_n) {
+    uint64_t w = GL_ROOT_2_32;
+    for (int i = log_n; i < 32; i++) w = sqr(w);
+    return w;
+}
+
+// x * 2^k for 0 <= k < 64 without a full multiply
+GL_HD uint64_t mul_pow2(uint64_t x, unsigned k) {
+    if (k == 0) return x;
+    return reduce128(x << k, x >> (64 - k));
+}
+
+// ---- Ext2 ----
+struct e2 {
+    uint64_t c0, c1;
+};
+GL_HD e2 make2(uint64_t a, uint64_t b) { e2 r; r.c0 = a; r.c1 = b; return r; }
+GL_HD e2 add(e2 a, e2 b) { return make2(add(a.c0, b.c0), add(a.c1, b.c1)); }
+GL_HD e2 sub(e2 a, e2 b) { return make2(sub(a.c0, b.c0), sub(a.c1, b.c1)); }
+GL_HD e2 neg(e2 a) { return make2(neg(a.c0), neg(a.c1)); }
+GL_HD e2 mul(e2 a, e2 b) {
+    uint64_t v0 = mul(a.c0, b.c0), v1 = mul(a.c1, b.c1);
+    // Karatsuba for the cross term: (a0+a1)(b0+b1) - v0 - v1
+    uint64_t cross = sub(sub(mul(add(a.c0, a.c1), add(b.c0, b.c1)), v0), v1);
+    uint64_t v1_7 = sub(mul_pow2(v1, 3), v1);
+    return make2(add(v0, v1_7), cross);
+}
+GL_HD e2 mul_base(e2 a, uint64_t b) { return make2(mul(a.c0, b), mul(a.c1, b)); }
+GL_HD e2 sqr(e2 a) { return mul(a, a); }
+GL_HD e2 inv(e2 a) {
+    uint64_t c1s = sqr(a.c1);
+    uint64_t n = sub(sqr(a.c0), sub(mul_pow2(c1s, 3), c1s));
+    uint64_t ni = inv(n);
+    return make2(mul(a.c0, ni), mul(neg(a.c1), ni));
+}
+GL_HD e2 pow(e2 b, uint64_t e) {
+    e2 r = make2(1, 0);
+    while (e) {
+        if (e & 1) r = mul(r, b);
+        b = sqr(b);
+        e >>= 1;
+    }
+    return r;
+}
+GL_HD bool eq(e2 a, e2 b) { return a.c0 == b.c0 && a.c1 == b.c1; }
+
+GL_HD uint32_t bitrev(uint32_t x, int bits) {
+#ifdef __CUDA_ARCH__
+    return bits ? (__brev(x) >> (32 - bits)) : 0;
+#else
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+    return r;
+#endif
+}
+
+}  // namespace gl

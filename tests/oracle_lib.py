@@ -1,0 +1,168 @@
+"""ctypes view of oracle/liboracle.so (CPU restatement of the reference algorithm -- the checker, test-only)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+P = (1 << 64) - (1 << 32) + 1
+c_u64 = ctypes.c_uint64
+vp = ctypes.c_void_p
+sz = ctypes.c_size_t
+ci = ctypes.c_int
+
+
+def build(force=False):
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+    return LIB
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        L = lib
+        L.orc_gl_pow.restype = c_u64; L.orc_gl_pow.argtypes = [c_u64, c_u64]
+        L.orc_gl_omega.restype = c_u64; L.orc_gl_omega.argtypes = [ci]
+        L.orc_lde_coset_shift.restype = c_u64; L.orc_lde_coset_shift.argtypes = [ci, ci, ctypes.c_uint32]
+        L.orc_ntt.argtypes = [vp, ci, ci]
+        L.orc_bitrev.argtypes = [vp, ci]
+        L.orc_coset_evals_bitrev.argtypes = [vp, ci, c_u64, vp]
+        L.orc_lde_from_values.argtypes = [vp, ci, ci, vp, vp]
+        L.orc_poseidon2_permute.argtypes = [vp]
+        L.orc_hash_leaf.argtypes = [vp, sz, vp]
+        L.orc_hash_node.argtypes = [vp, vp, vp]
+        L.orc_merkle_build.argtypes = [vp, sz, sz, sz, sz, sz, vp]
+        L.orc_merkle_path.argtypes = [vp, sz, sz, sz, vp]
+        L.orc_merkle_verify.restype = ci; L.orc_merkle_verify.argtypes = [vp, sz, vp, sz, vp, sz]
+        L.orc_fri_fold.argtypes = [vp, vp, ci, c_u64, vp, vp, vp]
+        L.orc_fri_fold_leaf.argtypes = [vp, vp, sz, ci, c_u64, sz, vp, vp]
+        L.orc_eval_ext_poly_at_base.argtypes = [vp, vp, sz, c_u64, vp]
+        for nm in ("orc_gl_mul_vec", "orc_gl_add_vec", "orc_gl_sub_vec", "orc_gl2_mul_vec"):
+            getattr(L, nm).argtypes = [vp, vp, vp, sz]
+        L.orc_gl_inv_vec.argtypes = [vp, vp, sz]
+        L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(vp)
+
+    def omega(self, log_n):
+        return int(self.lib.orc_gl_omega(log_n))
+
+    def pow(self, b, e):
+        return int(self.lib.orc_gl_pow(b, e))
+
+    def coset_shift(self, log_n, log_lde, c):
+        return int(self.lib.orc_lde_coset_shift(log_n, log_lde, c))
+
+    def ntt(self, a, inverse=False):
+        a = np.array(a, dtype=np.uint64)
+        log_n = int(a.shape[-1]).bit_length() - 1
+        flat = a.reshape(-1, a.shape[-1])
+        for row in flat:
+            self.lib.orc_ntt(self._p(row), log_n, 1 if inverse else 0)
+        return a
+
+    def coset_evals_bitrev(self, mono, shift):
+        mono = np.ascontiguousarray(mono, dtype=np.uint64)
+        out = np.empty_like(mono)
+        log_n = int(mono.shape[-1]).bit_length() - 1
+        m2, o2 = mono.reshape(-1, mono.shape[-1]), out.reshape(-1, mono.shape[-1])
+        for i in range(m2.shape[0]):
+            self.lib.orc_coset_evals_bitrev(self._p(m2[i]), log_n, shift, self._p(o2[i]))
+        return out
+
+    def lde(self, vals, log_lde):
+        vals = np.ascontiguousarray(vals, dtype=np.uint64)
+        n_cols, n = vals.shape
+        log_n = n.bit_length() - 1
+        out = np.empty((n_cols, n << log_lde), dtype=np.uint64)
+        mono = np.empty_like(vals)
+        for i in range(n_cols):
+            self.lib.orc_lde_from_values(self._p(vals[i]), log_n, log_lde, self._p(out[i]), self._p(mono[i]))
+        return mono, out
+
+    def permute(self, states):
+        s = np.array(states, dtype=np.uint64).reshape(-1, 12)
+        for row in s:
+            self.lib.orc_poseidon2_permute(self._p(row))
+        return s
+
+    def hash_leaf(self, els):
+        els = np.ascontiguousarray(els, dtype=np.uint64)
+        out = np.empty(4, dtype=np.uint64)
+        self.lib.orc_hash_leaf(self._p(els), els.size, self._p(out))
+        return out
+
+    def hash_node(self, l, r):
+        l = np.ascontiguousarray(l, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.uint64)
+        out = np.empty(4, dtype=np.uint64)
+        self.lib.orc_hash_node(self._p(l), self._p(r), self._p(out))
+        return out
+
+    def merkle_build(self, cols, n_leaves, elems_per_leaf, cap_size):
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        n_cols, stride = cols.shape
+        tree = np.empty((2 * n_leaves - cap_size, 4), dtype=np.uint64)
+        self.lib.orc_merkle_build(self._p(cols), stride, n_cols, n_leaves, elems_per_leaf, cap_size, self._p(tree))
+        return tree
+
+    def merkle_path(self, tree, n_leaves, cap_size, idx):
+        k = (n_leaves // cap_size).bit_length() - 1
+        out = np.empty((k, 4), dtype=np.uint64)
+        self.lib.orc_merkle_path(self._p(tree), n_leaves, cap_size, idx, self._p(out))
+        return out
+
+    def merkle_verify(self, leaf, path, cap, idx):
+        leaf = np.ascontiguousarray(leaf, dtype=np.uint64); path = np.ascontiguousarray(path, dtype=np.uint64)
+        cap = np.ascontiguousarray(cap, dtype=np.uint64)
+        return bool(self.lib.orc_merkle_verify(self._p(leaf), leaf.size, self._p(path), path.shape[0], self._p(cap), idx))
+
+    def fri_fold(self, c0, c1, log_dom, shift, ch):
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64); c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+        half = 1 << (log_dom - 1)
+        o0 = np.empty(half, dtype=np.uint64); o1 = np.empty(half, dtype=np.uint64)
+        chv = np.array(ch, dtype=np.uint64)
+        self.lib.orc_fri_fold(self._p(c0), self._p(c1), log_dom, shift, self._p(chv), self._p(o0), self._p(o1))
+        return o0, o1
+
+    def fri_fold_leaf(self, c0, c1, log_dom, shift, base_idx, ch):
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64); c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+        out = np.empty(2, dtype=np.uint64); chv = np.array(ch, dtype=np.uint64)
+        self.lib.orc_fri_fold_leaf(self._p(c0), self._p(c1), c0.size, log_dom, shift, base_idx, self._p(chv), self._p(out))
+        return int(out[0]), int(out[1])
+
+    def eval_ext_poly_at_base(self, c0, c1, x):
+        c0 = np.ascontiguousarray(c0, dtype=np.uint64); c1 = np.ascontiguousarray(c1, dtype=np.uint64)
+        out = np.empty(2, dtype=np.uint64)
+        self.lib.orc_eval_ext_poly_at_base(self._p(c0), self._p(c1), c0.size, x, self._p(out))
+        return int(out[0]), int(out[1])
+
+    def vec(self, name, *arrs):
+        arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]
+        out = np.empty_like(arrs[0])
+        n = arrs[0].size if "gl2" not in name else arrs[0].size // 2
+        getattr(self.lib, name)(*[self._p(a) for a in arrs], self._p(out), n)
+        return out
+
+
+_ORACLE = None
+
+
+def load():
+    global _ORACLE
+    if _ORACLE is None:
+        build()
+        _ORACLE = Oracle(ctypes.CDLL(LIB))
+    return _ORACLE
+
+
+def rand_field(rng, shape):
+    """uniform-ish canonical field elements (rejection of the 2^-32 tail is irrelevant: reduce mod p)"""
+    a = rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)
+    return np.where(a >= np.uint64(P), a - np.uint64(P), a)

@@ -1,0 +1,141 @@
+# Hash-free recovery of every FRI folding challenge and of each query's leaf index in every FRI oracle from a golden proof.
+import json, sys, itertools
+P=(1<<64)-(1<<32)+1
+G=0x185629dcda58878c
+def omega(k):
+    w=G
+    for _ in range(k,32): w=w*w%P
+    return w
+Z=(0,0); ONE=(1,0)
+def ea(a,b): return ((a[0]+b[0])%P,(a[1]+b[1])%P)
+def es(a,b): return ((a[0]-b[0])%P,(a[1]-b[1])%P)
+def em(a,b): return ((a[0]*b[0]+7*a[1]*b[1])%P,(a[0]*b[1]+a[1]*b[0])%P)
+def esc(a,s): return (a[0]*s%P,a[1]*s%P)
+def einv(a):
+    n=(a[0]*a[0]-7*a[1]*a[1])%P; ni=pow(n,P-2,P)
+    return (a[0]*ni%P,(-a[1])*ni%P)
+def brev(x,b): return int(format(x,'0%db'%b)[::-1],2) if b else 0
+# polynomials in c over GF(p^2): list of coeffs ascending
+def padd(a,b):
+    n=max(len(a),len(b)); a=a+[Z]*(n-len(a)); b=b+[Z]*(n-len(b)); return [ea(x,y) for x,y in zip(a,b)]
+def psub(a,b):
+    n=max(len(a),len(b)); a=a+[Z]*(n-len(a)); b=b+[Z]*(n-len(b)); return [es(x,y) for x,y in zip(a,b)]
+def pscale(a,s): return [esc(x,s) for x in a]
+def pshift(a,k): return [Z]*k+a
+def ptrim(a):
+    a=list(a)
+    while a and a[-1]==Z: a.pop()
+    return a
+def pmod(a,b):
+    a=ptrim(a); b=ptrim(b); 
+    if not b: raise ZeroDivisionError
+    inv=einv(b[-1])
+    while len(a)>=len(b):
+        f=em(a[-1],inv); d=len(a)-len(b)
+        for i,bc in enumerate(b): a[d+i]=es(a[d+i],em(f,bc))
+        a=ptrim(a)
+    return a
+def pgcd(a,b):
+    a=ptrim(a); b=ptrim(b)
+    while b: a,b=b,pmod(a,b)
+    return a
+def fold_poly(vals, log_dom, shift, base_idx, nsteps):
+    """vals: list of ext values at consecutive indices base_idx.. in a domain shift*<w_{2^log_dom}> (bitrev). Returns
+    polynomial in c (coeff list) of the fully folded value, with step i using c^(2^i)."""
+    cur=[[v] for v in vals]  # each a poly in c
+    s=shift; logd=log_dom; base=base_idx; e=1
+    for _ in range(nsteps):
+        nxt=[]
+        for k in range(len(cur)//2):
+            idx=base+2*k
+            x=s*pow(omega(logd),brev(idx,logd),P)%P; xinv=pow(x,P-2,P)
+            a,b=cur[2*k],cur[2*k+1]
+            nxt.append(padd(padd(a,b), pshift(pscale(psub(a,b),xinv),e)))
+        cur=nxt; e*=2; logd-=1; s=s*s%P; base//=2
+    return cur[0]
+def peval(p,c):
+    r=Z
+    for co in reversed(p): r=ea(em(r,c),co)
+    return r
+def analyse(path, log_lde_dom=21):
+    pr=json.load(open(path)); 
+    if 'proof_config' not in pr: pr=pr[list(pr.keys())[0]]
+    Q=pr['queries_per_fri_repetition']
+    mon=pr['final_fri_monomials']; poly=[(mon[0][i],mon[1][i]) for i in range(len(mon[0]))]
+    nor=len(Q[0]['fri_queries'])
+    leaf_sizes=[len(q['leaf_elements'])//2 for q in Q[0]['fri_queries']]
+    sched=[s.bit_length()-1 for s in leaf_sizes]
+    print("schedule",sched)
+    def leaf(q,k):
+        le=Q[q]['fri_queries'][k]['leaf_elements']; h=len(le)//2
+        return [(le[i],le[h+i]) for i in range(h)]
+    # domain sizes per oracle
+    logd=[log_lde_dom]
+    for s in sched: logd.append(logd[-1]-s)
+    shifts=[pow(7,1<<(log_lde_dom-l),P) for l in logd]
+    # final: value at final domain point index m_final (size 2^logd[-1])
+    nq=len(Q)
+    # last oracle: find c_last and leaf idx
+    k=nor-1
+    nleaves=1<<(logd[k]-sched[k])
+    def final_eval(idx):
+        pt=shifts[-1]*pow(omega(logd[-1]),brev(idx,logd[-1]),P)%P
+        r=Z
+        for co in reversed(poly): r=ea(esc(r,pt),co)
+        return r
+    # find challenge via gcd over two queries with different leaves
+    cands=None
+    qa=0; qb=next(i for i in range(1,nq) if leaf(i,k)!=leaf(0,k))
+    found=None
+    for ma in range(nleaves):
+        Fa=fold_poly(leaf(qa,k),logd[k],shifts[k],ma<<sched[k],sched[k]); Fa=psub(Fa,[final_eval(ma)])
+        for mb in range(nleaves):
+            Fb=fold_poly(leaf(qb,k),logd[k],shifts[k],mb<<sched[k],sched[k]); Fb=psub(Fb,[final_eval(mb)])
+            g=pgcd(Fa,Fb)
+            if len(g)==2:
+                c=esc(es(Z,g[0]),1); c=em(c,einv(g[1]))
+                # verify on all queries
+                ok=0; idxs=[]
+                for q in range(nq):
+                    hit=None
+                    for m in range(nleaves):
+                        F=fold_poly(leaf(q,k),logd[k],shifts[k],m<<sched[k],sched[k])
+                        if peval(F,c)==final_eval(m): hit=m
+                    idxs.append(hit); ok+= hit is not None
+                if ok==nq: found=(c,idxs)
+            if found: break
+        if found: break
+    chall=[None]*nor; leafidx=[None]*nor
+    chall[k],leafidx[k]=found
+    print("oracle",k,"challenge",chall[k])
+    # descend
+    for k in range(nor-2,-1,-1):
+        nxt_s=sched[k+1]
+        # query q: leaf idx m_k = (m_{k+1} << nxt_s?) hmm: next oracle leaf m_{k+1} holds 2^nxt_s points, each is the fold of one leaf of oracle k
+        def opts(q): return [ (leafidx[k+1][q]<<nxt_s)+j for j in range(1<<nxt_s)]
+        qa=0; qb=next(i for i in range(1,nq) if leaf(i,k)!=leaf(0,k))
+        found=None
+        for ma in opts(qa):
+            Fa=fold_poly(leaf(qa,k),logd[k],shifts[k],ma<<sched[k],sched[k]); Fa=psub(Fa,[leaf(qa,k+1)[ma&((1<<nxt_s)-1)]])
+            for mb in opts(qb):
+                Fb=fold_poly(leaf(qb,k),logd[k],shifts[k],mb<<sched[k],sched[k]); Fb=psub(Fb,[leaf(qb,k+1)[mb&((1<<nxt_s)-1)]])
+                g=pgcd(Fa,Fb)
+                if len(g)==2:
+                    c=em(es(Z,g[0]),einv(g[1]))
+                    idxs=[]; ok=0
+                    for q in range(nq):
+                        hit=None
+                        for m in opts(q):
+                            F=fold_poly(leaf(q,k),logd[k],shifts[k],m<<sched[k],sched[k])
+                            if peval(F,c)==leaf(q,k+1)[m&((1<<nxt_s)-1)]: hit=m
+                        idxs.append(hit); ok+=hit is not None
+                    if ok==nq: found=(c,idxs)
+                if found: break
+            if found: break
+        chall[k],leafidx[k]=found
+        print("oracle",k,"challenge",chall[k])
+    return dict(schedule=sched,challenges=chall,leaf_indexes=leafidx,log_domains=logd)
+if __name__=='__main__':
+    r=analyse(sys.argv[1])
+    json.dump(r,open(sys.argv[2],'w'))
+    print(r['leaf_indexes'][0][:10])

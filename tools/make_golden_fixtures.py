@@ -1,0 +1,58 @@
+#!/usr/bin/env python3
+"""Builds tests/golden/*.json from the reference's golden proofs (run in the build container, where /root/reference
+exists; the fixtures travel to the GPU box, the reference does not).
+
+fri_chain_<name>.json: for a golden proof, the FRI part of the first N queries (leaf elements of every FRI oracle),
+`final_fri_monomials`, and -- recovered WITHOUT the hash by tools/golden_fri_chain.py (polynomial gcd over GF(p^2))
+-- every folding challenge and each query's leaf index in every oracle.  All 100 queries of the proof are consistent
+with the recovered values, which pins: Ext2 = F[u]/(u^2-7), split leaf serialisation [c0.., c1..], LDE domain
+7*<omega>, bit-reversed enumeration, un-normalised fold with c, c^2, c^4 per oracle, folding schedule.
+"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from golden_fri_chain import analyse  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+PROOFS = {
+    "mainvm_1_0": "test_proofs/base_layer/basic_circuit_proof_1_0.json",
+    "ram_8_0": "test_proofs/base_layer/basic_circuit_proof_8_0.json",
+    "node_3_0_0": "test_proofs/recursion_layer/node_layer_proof_3_0_0.json",
+}
+N_QUERIES = 16
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for name, rel in PROOFS.items():
+        path = os.path.join(REF, rel)
+        res = analyse(path)
+        pr = json.load(open(path))
+        if "proof_config" not in pr:
+            pr = pr[list(pr.keys())[0]]
+        Q = pr["queries_per_fri_repetition"]
+        fx = {
+            "source": rel,
+            "proof_config": pr["proof_config"],
+            "schedule": res["schedule"],
+            "log_domains": res["log_domains"],
+            "challenges": res["challenges"],
+            "all_queries_consistent": all(all(i is not None for i in lv) for lv in res["leaf_indexes"]),
+            "n_queries_in_proof": len(Q),
+            "final_fri_monomials": pr["final_fri_monomials"],
+            "queries": [
+                {"leaf_indexes": [res["leaf_indexes"][k][q] for k in range(len(res["schedule"]))],
+                 "fri_leaves": [fq["leaf_elements"] for fq in Q[q]["fri_queries"]]}
+                for q in range(N_QUERIES)
+            ],
+        }
+        with open(os.path.join(OUT, f"fri_chain_{name}.json"), "w") as f:
+            json.dump(fx, f)
+        print(name, "ok", fx["all_queries_consistent"])
+
+
+if __name__ == "__main__":
+    main()
