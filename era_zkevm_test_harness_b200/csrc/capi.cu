@@ -77,12 +77,9 @@ int zkgpu_ctx_create(int device, void* cuda_stream, zkgpu_ctx** out) {
         if (prop.major < 10) throw zk::Error(3, "libzkgpu is built for sm_100a (Blackwell B200) only");
         zkgpu_ctx* ctx = new zkgpu_ctx();
         ctx->c.device = device;
-        if (cuda_stream) {
-            ctx->c.stream = (cudaStream_t)cuda_stream;
-        } else {
-            CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
-            ctx->c.own_stream = true;
-        }
+        // NULL is CUDA's own handle for the legacy default stream: work is then ordered with every other
+        // default-stream user of the process (e.g. torch's current stream when none was set).
+        ctx->c.stream = (cudaStream_t)cuda_stream;
         *out = ctx;
     });
 }

@@ -35,7 +35,7 @@ typedef struct zkgpu_ctx zkgpu_ctx;     /* one per GPU: device ordinal, stream, 
 typedef struct zkgpu_setup zkgpu_setup; /* device-resident per-circuit-type setup (replaces SetupStorage + setup tree) */
 
 /* ---- context (replaces `&Worker`, src/prover_utils.rs:50,207: the caller-owned execution resource) ---- */
-ZKGPU_API int zkgpu_ctx_create(int device, void* cuda_stream /* cudaStream_t or NULL for an owned stream */, zkgpu_ctx** out);
+ZKGPU_API int zkgpu_ctx_create(int device, void* cuda_stream /* cudaStream_t; NULL = the legacy default stream */, zkgpu_ctx** out);
 ZKGPU_API void zkgpu_ctx_destroy(zkgpu_ctx* ctx);
 ZKGPU_API int zkgpu_ctx_synchronize(zkgpu_ctx* ctx);
 ZKGPU_API uint64_t zkgpu_ctx_kernel_launches(const zkgpu_ctx* ctx); /* kernels launched through this context so far */
