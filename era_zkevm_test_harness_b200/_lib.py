@@ -25,6 +25,18 @@ SYMBOLS = {
     "zkgpu_merkle_build": (ci, [ctypes.c_void_p, u64p, sz, sz, sz, sz, sz, u64p]),
     "zkgpu_fri_fold": (ci, [ctypes.c_void_p, u64p, u64p, ci, u64, ctypes.POINTER(u64 * 2), u64p, u64p]),
     "zkgpu_commit_columns_host": (ci, [ctypes.c_void_p, u64p, sz, ci, ci, sz, u64p]),
+    "zkgpu_num_witness_cols": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "zkgpu_num_permuted_cols": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "zkgpu_num_setup_cols": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "zkgpu_num_stage2_cols": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "zkgpu_num_quotient_cols": (ctypes.c_uint32, [ctypes.c_void_p]),
+    "zkgpu_proof_size_u64": (sz, [ctypes.c_void_p, ctypes.c_void_p]),
+    "zkgpu_setup_create": (ci, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, u64p, ctypes.POINTER(ctypes.c_void_p), u64p]),
+    "zkgpu_setup_destroy": (None, [ctypes.c_void_p]),
+    "zkgpu_prove": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
+    "zkgpu_prove_device": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
+    "zkgpu_verify": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
+    "zkgpu_synth_trace": (ci, [ctypes.c_void_p, u64, u64p, u64p]),
 }
 
 _lib = None

@@ -1,0 +1,61 @@
+// host_common.cuh -- host-side pieces shared by the prover driver and the CPU verifier of libzkgpu.so:
+// geometry-derived shapes, the Poseidon2 transcript, proof buffer layout.
+//
+// Reference: these are the parts of boojum's `prove_from_precomputations` / `Verifier::verify`
+// (/root/reference/src/prover_utils.rs:338-372) that stay on the host in any implementation -- Fiat-Shamir transcript
+// (`GoldilocksPoisedon2Transcript`, prover_utils.rs:38), proof assembly (`Proof<F,H,EXT>`, field order as in the golden
+// JSON files under /root/reference/test_proofs/).
+#pragma once
+#include <cstring>
+#include <vector>
+#include "../../include/zkgpu.h"
+#include "gates.cuh"
+#include "zk_internal.cuh"
+
+namespace zk {
+
+// ---- host Poseidon2 (same parameters as poseidon2.cu) ----
+extern const uint64_t H_P2_RC[360];
+void host_poseidon2_permute(uint64_t (&s)[12]);
+void host_hash_leaf(const uint64_t* els, size_t n, uint64_t out[4]);
+void host_hash_node(const uint64_t* l, const uint64_t* r, uint64_t out[4]);
+
+inline uint32_t ilog2(size_t x) { uint32_t r = 0; while (((size_t)1 << r) < x) r++; return r; }
+
+struct Shape {
+    size_t N, LN, depth;
+    uint32_t log_n, log_lde, W, S, S2, Q, NP, C, E2, QD, n_at_z, n_at_zw, n_at_0, n_final, n_terms, NF;
+    uint32_t lookup_col0;  // first lookup column inside the witness
+    size_t fri_dom_log[ZKGPU_MAX_FRI_ORACLES + 1], fri_leaves[ZKGPU_MAX_FRI_ORACLES], fri_cap[ZKGPU_MAX_FRI_ORACLES],
+        fri_depth[ZKGPU_MAX_FRI_ORACLES];
+    size_t proof_len;
+};
+Shape make_shape(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
+void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
+
+constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;
+
+struct Transcript {
+    uint64_t st[12] = {0};
+    std::vector<uint64_t> buf;
+    int pos = 8;
+    void absorb(const uint64_t* v, size_t n) { buf.insert(buf.end(), v, v + n); }
+    void absorb(const gl::e2& e) { buf.push_back(e.c0); buf.push_back(e.c1); }
+    uint64_t challenge() {
+        if (!buf.empty()) {
+            for (size_t i = 0; i < buf.size(); i += 8) {
+                for (size_t k = 0; k < 8; k++) st[k] = i + k < buf.size() ? buf[i + k] : 0;
+                host_poseidon2_permute(st);
+            }
+            buf.clear();
+            pos = 0;
+        } else if (pos == 8) {
+            host_poseidon2_permute(st);
+            pos = 0;
+        }
+        return st[pos++];
+    }
+    gl::e2 challenge_ext() { uint64_t a = challenge(); uint64_t b = challenge(); return gl::make2(a, b); }
+};
+
+}  // namespace zk

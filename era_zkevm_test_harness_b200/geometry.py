@@ -1,0 +1,257 @@
+"""Circuit geometry, gate tables and proof configs -- the host-side mirror of the reference's
+`circuit_definitions` shapes as ctypes structs of include/zkgpu.h.
+
+Reference:
+  * geometry per circuit: circuit_definitions/src/circuit_definitions/base_layer/*.rs (`geometry()`, `lookup_parameters()`,
+    `configure_builder()`), recursion_layer/{circuit_def,scheduler}.rs
+  * proof configs: circuit_definitions/src/lib.rs:13-57 (`base_layer_proof_config()` ...)
+  * VK JSON (`VerificationKey.fixed_parameters`): setup/base_layer/vk_N.json, setup/recursion_layer/vk_*.json
+"""
+import ctypes
+import json
+import math
+
+MAX_GATES = 24
+MAX_PI = 8
+MAX_FRI = 16
+
+# gate kinds (include/zkgpu.h)
+(GATE_NOP, GATE_CONSTANTS_ALLOCATOR, GATE_FMA, GATE_REDUCTION4, GATE_SELECTION, GATE_PARALLEL_SELECTION4, GATE_ZERO_CHECK,
+ GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT) = range(12)
+
+GATE_NAMES = {
+    "ConstantsAllocator": GATE_CONSTANTS_ALLOCATOR, "FmaBaseNoConst": GATE_FMA, "Reduction4": GATE_REDUCTION4,
+    "Selection": GATE_SELECTION, "ParallelSelection4": GATE_PARALLEL_SELECTION4, "ZeroCheck": GATE_ZERO_CHECK,
+    "UIntXAdd": GATE_UINTX_ADD, "DotProduct4": GATE_DOT_PRODUCT4, "U8x4FMA": GATE_U8X4_FMA,
+    "Poseidon2Flattened": GATE_POSEIDON2_FLATTENED, "FmaExt": GATE_FMA_EXT, "PublicInput": GATE_NOP, "Nop": GATE_NOP,
+    "U32TriAddCarryAsChunk": GATE_NOP,  # StorageApplication only; relation not restated yet (DESIGN.md "Out of scope")
+}
+
+# gate_idx -> gate name per verification key, derived in SURVEY.md section 8a by matching each VK's
+# (num_constants, degree) list against the configure_builder order of the circuit
+BASE_LAYER_GATE_ORDER = {
+    1: ["ConstantsAllocator", "U8x4FMA", "Poseidon2Flattened", "DotProduct4", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "Selection",
+        "ParallelSelection4", "PublicInput", "Reduction4"],
+    7: ["ConstantsAllocator", "U8x4FMA", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "DotProduct4", "Selection", "ParallelSelection4",
+        "PublicInput", "Reduction4"],
+    10: ["ConstantsAllocator", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "U32TriAddCarryAsChunk", "Selection", "ParallelSelection4",
+         "PublicInput", "Reduction4"],
+}
+for _t in (2, 4, 8, 9, 11, 12):
+    BASE_LAYER_GATE_ORDER[_t] = ["ConstantsAllocator", "Poseidon2Flattened", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "Selection",
+                                 "ParallelSelection4", "PublicInput", "Reduction4"]
+for _t in (3, 6):
+    BASE_LAYER_GATE_ORDER[_t] = ["ConstantsAllocator", "FmaBaseNoConst", "Reduction4", "Selection", "ParallelSelection4", "PublicInput",
+                                 "UIntXAdd", "ZeroCheck"]
+for _t in (5, 13):
+    BASE_LAYER_GATE_ORDER[_t] = ["ConstantsAllocator", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "Selection", "ParallelSelection4",
+                                 "PublicInput", "Reduction4"]
+RECURSION_GATE_ORDER = ["ConstantsAllocator", "Poseidon2Flattened", "ZeroCheck", "FmaBaseNoConst", "FmaExt", "UIntXAdd", "Selection",
+                        "ParallelSelection4", "PublicInput", "Reduction4"]
+
+BASE_LAYER_CIRCUIT_NAMES = {
+    1: "MainVM", 2: "CodeDecommittmentsSorter", 3: "CodeDecommitter", 4: "LogDemuxer", 5: "KeccakRoundFunction", 6: "Sha256RoundFunction",
+    7: "ECRecover", 8: "RAMPermutation", 9: "StorageSorter", 10: "StorageApplication", 11: "EventsSorter", 12: "L1MessagesSorter",
+    13: "L1MessagesHasher",
+}
+
+
+class Gate(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_uint32), ("n_consts", ctypes.c_uint32), ("path_len", ctypes.c_uint32), ("path_bits", ctypes.c_uint32)]
+
+
+class Geometry(ctypes.Structure):
+    _fields_ = [("log_n", ctypes.c_uint32), ("n_copy", ctypes.c_uint32), ("n_const_cols", ctypes.c_uint32),
+                ("lookup_width", ctypes.c_uint32), ("lookup_reps", ctypes.c_uint32), ("table_id_col", ctypes.c_uint32),
+                ("has_boolean_col", ctypes.c_uint32), ("quotient_degree", ctypes.c_uint32), ("table_len", ctypes.c_uint32),
+                ("n_public_inputs", ctypes.c_uint32), ("pi_col", ctypes.c_uint32 * MAX_PI), ("pi_row", ctypes.c_uint32 * MAX_PI),
+                ("n_gates", ctypes.c_uint32), ("gates", Gate * MAX_GATES)]
+
+    # derived counts (same formulas as csrc/host.cu make_shape)
+    @property
+    def n_perm(self):
+        return self.n_copy + (1 if self.has_boolean_col else 0) + self.lookup_width * self.lookup_reps
+
+    @property
+    def n_witness(self):
+        return self.n_perm + (1 if self.lookup_reps else 0)
+
+    @property
+    def n_setup(self):
+        return self.n_perm + self.n_const_cols + (self.lookup_width + 1 if self.lookup_reps else 0)
+
+    @property
+    def n_stage2(self):
+        c = (self.n_perm + self.quotient_degree - 1) // self.quotient_degree
+        return 2 * (c + self.lookup_reps + (1 if self.lookup_reps else 0))
+
+    @property
+    def n_quotient(self):
+        return 2 * self.quotient_degree
+
+    def scaled(self, log_n, table_len=None):
+        """same circuit shape on a shorter trace (parity-test sizes); public-input rows and table length are clamped"""
+        g = Geometry.from_buffer_copy(bytes(self))
+        g.log_n = log_n
+        n = 1 << log_n
+        for i in range(g.n_public_inputs):
+            g.pi_row[i] = self.pi_row[i] % n
+        g.table_len = min(self.table_len, n // 2) if table_len is None else table_len
+        return g
+
+
+class ProofConfig(ctypes.Structure):
+    _fields_ = [("log_lde", ctypes.c_uint32), ("cap_size", ctypes.c_uint32), ("n_queries", ctypes.c_uint32), ("pow_bits", ctypes.c_uint32),
+                ("n_fri_oracles", ctypes.c_uint32), ("fri_schedule", ctypes.c_uint32 * MAX_FRI)]
+
+
+def fri_schedule(log_n, log_lde, cap_size, final_log_degree=3):
+    """Folding schedule as the golden proofs show it: fold by 8 while the next oracle still has at
+    least cap_size leaves, close with a smaller fold, stop at a final polynomial of 2^final_log_degree coefficients.
+    2^20, lde 2, cap 16 -> [3,3,3,3,3,2]."""
+    total = max(log_n - final_log_degree, 1)
+    log_dom = log_n + log_lde
+    sched = []
+    while total > 0:
+        s = min(3, total)
+        # an oracle over 2^log_dom points with leaves of 2^s points needs >= cap_size leaves
+        while s > 1 and (1 << (log_dom - s)) < cap_size:
+            s -= 1
+        sched.append(s)
+        total -= s
+        log_dom -= s
+    return sched
+
+
+def make_proof_config(log_n, fri_lde_factor=2, merkle_tree_cap_size=16, security_level=100, pow_bits=0, schedule=None):
+    """ProofConfig{fri_lde_factor, merkle_tree_cap_size, fri_folding_schedule: None, security_level, pow_bits}
+    (circuit_definitions/src/lib.rs:29-37) -> derived query count and folding schedule."""
+    log_lde = int(math.log2(fri_lde_factor))
+    assert 1 << log_lde == fri_lde_factor
+    cfg = ProofConfig()
+    cfg.log_lde = log_lde
+    cfg.cap_size = merkle_tree_cap_size
+    cfg.n_queries = -(-security_level // log_lde)
+    cfg.pow_bits = pow_bits
+    sched = fri_schedule(log_n, log_lde, merkle_tree_cap_size) if schedule is None else list(schedule)
+    cfg.n_fri_oracles = len(sched)
+    for i, s in enumerate(sched):
+        cfg.fri_schedule[i] = s
+    return cfg
+
+
+def base_layer_proof_config(log_n=20):
+    """circuit_definitions/src/lib.rs:29-37: lde 2, cap 16, security 100, pow 0"""
+    return make_proof_config(log_n, 2, 16, 100, 0)
+
+
+recursion_layer_proof_config = base_layer_proof_config  # lib.rs:39-47 -- same constants
+
+
+def _walk_selector_tree(node, path, out):
+    """selectors_placement is {"Fork": {"left": .., "right": ..}} / {"GateOnly": {"gate_idx", "num_constants", "degree_of_gate", ..}} /
+    "Empty"; left = constant bit 0, right = bit 1 (MainVM: Poseidon2Flattened sits at path [0], ConstantsAllocator at [1,1,1])"""
+    if node == "Empty" or node is None:
+        return
+    if "Fork" in node:
+        f = node["Fork"]
+        _walk_selector_tree(f["left"], path + [0], out)
+        _walk_selector_tree(f["right"], path + [1], out)
+        return
+    g = node.get("GateOnly") or node.get("Gate") or node
+    out.append((g["gate_idx"], g["num_constants"], g.get("degree_of_gate", g.get("degree")), list(path)))
+
+
+def geometry_from_vk(vk, gate_order):
+    """vk: the inner dict of a VK JSON file ({"fixed_parameters": .., "setup_merkle_tree_cap": ..});
+    gate_order: gate names by gate_idx (BASE_LAYER_GATE_ORDER[type] / RECURSION_GATE_ORDER)."""
+    fp = vk["fixed_parameters"]
+    par = fp["parameters"]
+    g = Geometry()
+    g.log_n = int(math.log2(fp["domain_size"]))
+    g.n_copy = par["num_columns_under_copy_permutation"]
+    assert par["num_witness_columns"] == 0, "non-copied witness columns are not used by any reference circuit"
+    lp = fp["lookup_parameters"]
+    if lp == "NoLookup":
+        g.lookup_width = g.lookup_reps = 0
+    else:
+        (kind, body), = lp.items()
+        assert kind == "UseSpecializedColumnsWithTableIdAsConstant", kind
+        g.lookup_width, g.lookup_reps = body["width"], body["num_repetitions"]
+    g.n_const_cols = par["num_constant_columns"] + fp["extra_constant_polys_for_selectors"] + (1 if g.lookup_reps else 0)
+    g.table_id_col = fp["table_ids_column_idxes"][0] if g.lookup_reps else 0
+    g.has_boolean_col = 1 if g.lookup_reps or True else 0  # every reference circuit places BooleanConstraintGate in its own column
+    g.quotient_degree = fp["quotient_degree"]
+    g.table_len = fp["total_tables_len"]
+    pis = fp["public_inputs_locations"]
+    g.n_public_inputs = len(pis)
+    for i, (col, row) in enumerate(pis):
+        g.pi_col[i], g.pi_row[i] = col, row
+    gates = []
+    _walk_selector_tree(fp["selectors_placement"], [], gates)
+    gates.sort()
+    g.n_gates = len(gates)
+    for i, (idx, n_consts, _deg, path) in enumerate(gates):
+        assert idx == i, "gate indexes are expected to be dense"
+        g.gates[i].kind = GATE_NAMES[gate_order[idx]]
+        g.gates[i].n_consts = n_consts
+        g.gates[i].path_len = len(path)
+        g.gates[i].path_bits = sum(b << k for k, b in enumerate(path))
+    return g
+
+
+def load_vk_json(path):
+    d = json.load(open(path))
+    if "fixed_parameters" not in d:
+        (name, d), = d.items()
+    else:
+        name = None
+    return name, d
+
+
+def mainvm_like_geometry(log_n=20):
+    """MainVM shape without reading the reference: 130 copy cols, lookup 3x8, 7+1 constant
+    columns, the 11 gates of vk_1.json with their selector paths, quotient degree 8, 4 public inputs."""
+    g = Geometry()
+    g.log_n = log_n
+    g.n_copy, g.n_const_cols = 130, 8
+    g.lookup_width, g.lookup_reps, g.table_id_col = 3, 8, 7
+    g.has_boolean_col, g.quotient_degree = 1, 8
+    g.table_len = min(68756, (1 << log_n) // 2)
+    g.n_public_inputs = 4
+    for i in range(4):
+        g.pi_col[i], g.pi_row[i] = i, 1033357 % (1 << log_n)
+    spec = [("ConstantsAllocator", 4, "111"), ("U8x4FMA", 0, "100100"), ("Poseidon2Flattened", 0, "0"), ("DotProduct4", 0, "100010"),
+            ("ZeroCheck", 0, "100011"), ("FmaBaseNoConst", 2, "10000"), ("UIntXAdd", 1, "101"), ("Selection", 0, "100110"),
+            ("ParallelSelection4", 0, "100101"), ("PublicInput", 0, "100111"), ("Reduction4", 4, "110")]
+    g.n_gates = len(spec)
+    for i, (name, nc, path) in enumerate(spec):
+        g.gates[i].kind = GATE_NAMES[name]
+        g.gates[i].n_consts = nc
+        g.gates[i].path_len = len(path)
+        g.gates[i].path_bits = sum(int(b) << k for k, b in enumerate(path))
+    return g
+
+
+def small_test_geometry(log_n=8, n_copy=16, lookup=True):
+    """a tiny circuit for fast CPU tests: FMA / Reduction / Selection / ZeroCheck / UIntXAdd / ConstantsAllocator"""
+    g = Geometry()
+    g.log_n = log_n
+    g.n_copy = n_copy
+    g.n_const_cols = 8 if lookup else 7
+    if lookup:
+        g.lookup_width, g.lookup_reps, g.table_id_col = 3, 2, 7
+        g.table_len = (1 << log_n) // 4
+    g.has_boolean_col, g.quotient_degree = 1, 8
+    g.n_public_inputs = 2
+    for i in range(2):
+        g.pi_col[i], g.pi_row[i] = i, (1 << log_n) - 3
+    spec = [("ConstantsAllocator", 4, "111"), ("FmaBaseNoConst", 2, "10000"), ("Reduction4", 4, "110"), ("Selection", 0, "100110"),
+            ("ZeroCheck", 0, "100011"), ("UIntXAdd", 1, "101"), ("PublicInput", 0, "100111"), ("DotProduct4", 0, "100010")]
+    g.n_gates = len(spec)
+    for i, (name, nc, path) in enumerate(spec):
+        g.gates[i].kind = GATE_NAMES[name]
+        g.gates[i].n_consts = nc
+        g.gates[i].path_len = len(path)
+        g.gates[i].path_bits = sum(int(b) << k for k, b in enumerate(path))
+    return g

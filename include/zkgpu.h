@@ -72,6 +72,102 @@ ZKGPU_API int zkgpu_fri_fold(zkgpu_ctx* ctx, const uint64_t* d_in_c0, const uint
 ZKGPU_API int zkgpu_commit_columns_host(zkgpu_ctx* ctx, const uint64_t* h_cols, size_t n_cols, int log_n, int log_lde, size_t cap_size,
                               uint64_t* h_cap_out);
 
+
+/* ==================================================================================================================
+ * Circuit description, setup, prove, verify  (the drop-in for get_full_setup / prove_from_precomputations / verify)
+ * ================================================================================================================== */
+
+/* Gate kinds.  The VK (setup/base_layer/vk_N.json: fixed_parameters.selectors_placement) stores per gate only
+ * (gate_idx, num_constants, degree) and the selector path; the gate polynomials are boojum source.  The kinds below
+ * restate the gate set named by the reference's configure_builder calls (circuit_definitions/src/circuit_definitions/
+ * base_layer/vm_main.rs:55-117 and siblings); SURVEY.md section 8a maps gate_idx -> kind for every VK. */
+enum {
+    ZKGPU_GATE_NOP = 0,               /* NopGate / PublicInputGate: no relation                                   */
+    ZKGPU_GATE_CONSTANTS_ALLOCATOR,   /* v_i - k_i, one instance per gate constant                       (deg 1) */
+    ZKGPU_GATE_FMA,                   /* k0*a*b + k1*c - d                     FmaGateInBaseFieldWithoutConstant  */
+    ZKGPU_GATE_REDUCTION4,            /* sum_i k_i*a_i - out                                   ReductionGate<_,4> */
+    ZKGPU_GATE_SELECTION,             /* s*a + (1-s)*b - out                                        SelectionGate */
+    ZKGPU_GATE_PARALLEL_SELECTION4,   /* 4x selection with a shared selector                ParallelSelectionGate */
+    ZKGPU_GATE_ZERO_CHECK,            /* x*inv - (1-z), x*z                                         ZeroCheckGate */
+    ZKGPU_GATE_UINTX_ADD,             /* a + b + cin - c - k*cout, cout^2 - cout                     UIntXAddGate */
+    ZKGPU_GATE_DOT_PRODUCT4,          /* sum_i a_i*b_i - out                                   DotProductGate<4> */
+    ZKGPU_GATE_U8X4_FMA,              /* byte-decomposed a*b + c + carry = low + 2^32*high               U8x4FMAGate */
+    ZKGPU_GATE_POSEIDON2_FLATTENED,   /* one whole Poseidon2 permutation per row, 118 relations of degree 7       */
+    ZKGPU_GATE_FMA_EXT,               /* FMA over Ext2 (4 constants)                FmaGateInExtensionWithoutConstant */
+    ZKGPU_GATE_KINDS
+};
+
+#define ZKGPU_MAX_GATES 24
+#define ZKGPU_MAX_PUBLIC_INPUTS 8
+#define ZKGPU_MAX_FRI_ORACLES 16
+
+typedef struct {
+    uint32_t kind;       /* ZKGPU_GATE_* */
+    uint32_t n_consts;   /* gate constants, read from constant columns [path_len, path_len + n_consts) */
+    uint32_t path_len;   /* selector = prod over i < path_len of (c_i if bit i of path_bits else 1 - c_i) */
+    uint32_t path_bits;
+} zkgpu_gate;
+
+/* Mirrors VerificationKey.fixed_parameters (boojum VerificationKeyCircuitGeometry) as read from setup/ vk_N.json. */
+typedef struct {
+    uint32_t log_n;             /* domain_size = 2^log_n                                                           */
+    uint32_t n_copy;            /* parameters.num_columns_under_copy_permutation                                    */
+    uint32_t n_const_cols;      /* num_constant_columns + extra_constant_polys_for_selectors (+1 table-id column)   */
+    uint32_t lookup_width;      /* lookup_parameters width (0 = no lookup)                                          */
+    uint32_t lookup_reps;       /* num_repetitions                                                                  */
+    uint32_t table_id_col;      /* table_ids_column_idxes[0]: constant column carrying the row's table id           */
+    uint32_t has_boolean_col;   /* one specialised boolean-constrained column (the Boolean gate's own column)       */
+    uint32_t quotient_degree;   /* quotient_degree (8)                                                              */
+    uint32_t table_len;         /* total_tables_len                                                                 */
+    uint32_t n_public_inputs;
+    uint32_t pi_col[ZKGPU_MAX_PUBLIC_INPUTS], pi_row[ZKGPU_MAX_PUBLIC_INPUTS]; /* public_inputs_locations */
+    uint32_t n_gates;
+    zkgpu_gate gates[ZKGPU_MAX_GATES];
+} zkgpu_geometry;
+
+/* Mirrors ProofConfig (circuit_definitions/src/lib.rs:29-57) with the derived query count and folding schedule. */
+typedef struct {
+    uint32_t log_lde;           /* log2(fri_lde_factor) */
+    uint32_t cap_size;          /* merkle_tree_cap_size */
+    uint32_t n_queries;         /* ceil(security_level / log2(fri_lde_factor)) */
+    uint32_t pow_bits;          /* 0 everywhere in the reference (NoPow) */
+    uint32_t n_fri_oracles;     /* base oracle + intermediates */
+    uint32_t fri_schedule[ZKGPU_MAX_FRI_ORACLES]; /* log2 fold factor per oracle, e.g. 3,3,3,3,3,2 */
+} zkgpu_proof_config;
+
+/* derived column counts (identical formulas in prover, verifier and oracle) */
+ZKGPU_API uint32_t zkgpu_num_witness_cols(const zkgpu_geometry* g);  /* n_copy + boolean + width*reps + multiplicity */
+ZKGPU_API uint32_t zkgpu_num_permuted_cols(const zkgpu_geometry* g); /* witness columns under copy permutation     */
+ZKGPU_API uint32_t zkgpu_num_setup_cols(const zkgpu_geometry* g);    /* sigmas + constants + (width+1) table cols   */
+ZKGPU_API uint32_t zkgpu_num_stage2_cols(const zkgpu_geometry* g);   /* 2 * (ceil(perm/qdeg) + reps + (reps?1:0))   */
+ZKGPU_API uint32_t zkgpu_num_quotient_cols(const zkgpu_geometry* g); /* 2 * quotient_degree                         */
+ZKGPU_API size_t zkgpu_proof_size_u64(const zkgpu_geometry* g, const zkgpu_proof_config* cfg); /* proof buffer length */
+
+/* get_full_setup (src/prover_utils.rs:185-186): uploads the setup columns (column-major, natural row order:
+ * sigma columns, constant columns, table columns -- zkgpu_num_setup_cols() x 2^log_n), keeps monomials + LDE +
+ * Merkle tree resident on the GPU, returns the VK's setup_merkle_tree_cap (cap_size*4 u64). */
+ZKGPU_API int zkgpu_setup_create(zkgpu_ctx* ctx, const zkgpu_geometry* g, const zkgpu_proof_config* cfg, const uint64_t* h_setup_cols,
+                                 zkgpu_setup** out, uint64_t* h_vk_cap_out);
+ZKGPU_API void zkgpu_setup_destroy(zkgpu_setup* s);
+
+/* prove_from_precomputations (src/prover_utils.rs:338-348): h_witness_cols = zkgpu_num_witness_cols() x 2^log_n
+ * (column-major, natural row order, the materialised trace: copy columns, boolean column, lookup columns,
+ * multiplicities).  Writes the proof (layout: DESIGN.md "Proof buffer") into h_proof_out. */
+ZKGPU_API int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_cols, uint64_t* h_proof_out,
+                          size_t proof_capacity_u64);
+/* same, witness already resident on the device (d_witness_cols, column stride = 2^log_n) */
+ZKGPU_API int zkgpu_prove_device(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* d_witness_cols, uint64_t* h_proof_out,
+                                 size_t proof_capacity_u64);
+
+/* Verifier::verify (src/prover_utils.rs:351-372): CPU only, as in the reference. Returns 0 iff the proof is valid,
+ * 1 if invalid (message says which check failed), >1 on malformed input. */
+ZKGPU_API int zkgpu_verify(const zkgpu_geometry* g, const zkgpu_proof_config* cfg, const uint64_t* vk_cap, const uint64_t* proof,
+                           size_t proof_len_u64);
+
+/* Synthetic satisfying trace for a geometry (stands in for the reference's Rust synthesis, which cannot run in this
+ * image): fills witness (W x n) and setup (S x n) columns deterministically from `seed`.  Host only. */
+ZKGPU_API int zkgpu_synth_trace(const zkgpu_geometry* g, uint64_t seed, uint64_t* h_witness_cols, uint64_t* h_setup_cols);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,11 @@ class Oracle:
         for nm in ("orc_gl_mul_vec", "orc_gl_add_vec", "orc_gl_sub_vec", "orc_gl2_mul_vec"):
             getattr(L, nm).argtypes = [vp, vp, vp, sz]
         L.orc_gl_inv_vec.argtypes = [vp, vp, sz]
+        L.orc_proof_size_u64.restype = sz; L.orc_proof_size_u64.argtypes = [vp, vp]
+        L.orc_setup_cap.argtypes = [vp, vp, vp, vp]
+        L.orc_prove.restype = ctypes.c_long; L.orc_prove.argtypes = [vp, vp, vp, vp, vp, sz]
+        for nm in ("orc_num_witness_cols", "orc_num_setup_cols", "orc_num_stage2_cols"):
+            getattr(L, nm).restype = ctypes.c_uint32; getattr(L, nm).argtypes = [vp]
         L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
 
     @staticmethod
@@ -142,6 +147,21 @@ class Oracle:
         out = np.empty(2, dtype=np.uint64)
         self.lib.orc_eval_ext_poly_at_base(self._p(c0), self._p(c1), c0.size, x, self._p(out))
         return int(out[0]), int(out[1])
+
+    # ---- whole-prover restatement (oracle/prover.c); geo/cfg are ctypes structs of include/zkgpu.h
+    def setup_cap(self, geo, cfg, setup_cols):
+        setup_cols = np.ascontiguousarray(setup_cols, dtype=np.uint64)
+        cap = np.empty((cfg.cap_size, 4), dtype=np.uint64)
+        self.lib.orc_setup_cap(ctypes.byref(geo), ctypes.byref(cfg), self._p(setup_cols), self._p(cap))
+        return cap
+
+    def prove(self, geo, cfg, wit_cols, setup_cols):
+        wit_cols = np.ascontiguousarray(wit_cols, dtype=np.uint64); setup_cols = np.ascontiguousarray(setup_cols, dtype=np.uint64)
+        n = int(self.lib.orc_proof_size_u64(ctypes.byref(geo), ctypes.byref(cfg)))
+        proof = np.zeros(n, dtype=np.uint64)
+        w = self.lib.orc_prove(ctypes.byref(geo), ctypes.byref(cfg), self._p(wit_cols), self._p(setup_cols), self._p(proof), n)
+        assert w == n, (w, n)
+        return proof
 
     def vec(self, name, *arrs):
         arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]
