@@ -80,6 +80,11 @@ int zkgpu_ctx_create(int device, void* cuda_stream, zkgpu_ctx** out) {
         // NULL is CUDA's own handle for the legacy default stream: work is then ordered with every other
         // default-stream user of the process (e.g. torch's current stream when none was set).
         ctx->c.stream = (cudaStream_t)cuda_stream;
+        // keep freed stream-ordered allocations cached in the pool: a proof allocates and frees tens of GB of scratch
+        cudaMemPool_t pool;
+        CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ULL;
+        CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         *out = ctx;
     });
 }
