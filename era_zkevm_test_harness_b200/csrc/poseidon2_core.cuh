@@ -1,0 +1,77 @@
+// poseidon2_core.cuh -- the Poseidon2-Goldilocks permutation (width 12, x^7, 4 + 22 + 4 rounds) on lazy residues.
+//
+// Same function as oracle/primitives.c:orc_poseidon2_permute (the tree/transcript hash `H` of the reference,
+// /root/reference/src/prover_utils.rs:43), restructured for the GPU integer pipes:
+//   * state lanes are arbitrary u64 representatives (glx.cuh); nothing is canonicalised between rounds,
+//   * both linear layers are computed as exact 96-bit integer combinations (coefficients are tiny) followed by one
+//     reduce96 per lane instead of ~60 modular additions per layer,
+//   * the caller canonicalises only the lanes that leave the kernel.
+// RC is any indexable holder of the 360 round constants (a __constant__ array on the device, a plain array on the host,
+// which is how tests/test_lazy_poseidon_cpu.py checks this header against the oracle without a GPU).
+#pragma once
+#include "glx.cuh"
+
+namespace zk {
+
+// y = circ(2*M4, M4, M4) * x,  M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]; integer result < 64 * 2^64
+GL_HD void p2x_external(uint64_t (&s)[12]) {
+    glx::w96 y[12];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        glx::w96 x0 = glx::widen(s[4 * b]), x1 = glx::widen(s[4 * b + 1]), x2 = glx::widen(s[4 * b + 2]), x3 = glx::widen(s[4 * b + 3]);
+        glx::w96 t0 = glx::add(x0, x1), t1 = glx::add(x2, x3);
+        glx::w96 t2 = glx::add(glx::shl(x1, 1), t1), t3 = glx::add(glx::shl(x3, 1), t0);
+        glx::w96 t4 = glx::add(glx::shl(t1, 2), t3), t5 = glx::add(glx::shl(t0, 2), t2);
+        y[4 * b] = glx::add(t3, t5);
+        y[4 * b + 1] = t5;
+        y[4 * b + 2] = glx::add(t2, t4);
+        y[4 * b + 3] = t4;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        glx::w96 t = glx::add(glx::add(y[i], y[4 + i]), y[8 + i]);
+        s[i] = glx::reduce(glx::add(y[i], t));
+        s[4 + i] = glx::reduce(glx::add(y[4 + i], t));
+        s[8 + i] = glx::reduce(glx::add(y[8 + i], t));
+    }
+}
+
+// y_i = 2^sh_i * x_i + sum(x),  sh = [4,14,11,8,0,5,2,9,13,6,3,12]; integer result < (2^14 + 12) * 2^64
+GL_HD void p2x_internal(uint64_t (&s)[12]) {
+    constexpr unsigned SH[12] = {4, 14, 11, 8, 0, 5, 2, 9, 13, 6, 3, 12};
+    glx::w96 sum = glx::widen(s[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) sum = glx::add(sum, s[i]);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        glx::w96 x = glx::widen(s[i]);
+        if (SH[i]) x = glx::shl(x, SH[i]);
+        s[i] = glx::reduce(glx::add(x, sum));
+    }
+}
+
+// in: any representatives; out: any representatives (canonicalise what you export)
+template <typename RC>
+GL_HD void p2x_permute(uint64_t (&s)[12], const RC& rc) {
+    p2x_external(s);
+    int r = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = glx::pow7(glx::add_canon(s[i], rc[12 * r + i]));
+        p2x_external(s);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 22; k++, r++) {
+        s[0] = glx::pow7(glx::add_canon(s[0], rc[12 * r]));
+        p2x_internal(s);
+    }
+#pragma unroll 1
+    for (int k = 0; k < 4; k++, r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = glx::pow7(glx::add_canon(s[i], rc[12 * r + i]));
+        p2x_external(s);
+    }
+}
+
+}  // namespace zk

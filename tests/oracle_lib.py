@@ -186,3 +186,20 @@ def rand_field(rng, shape):
     """uniform-ish canonical field elements (rejection of the 2^-32 tail is irrelevant: reduce mod p)"""
     a = rng.integers(0, 1 << 63, size=shape, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=shape, dtype=np.uint64)
     return np.where(a >= np.uint64(P), a - np.uint64(P), a)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# hostcheck: the HOST halves of the product's device headers (glx.cuh lazy arithmetic, poseidon2_core.cuh) compiled with
+# g++ so the CPU suite can check them against the oracle without a GPU.
+HOSTCHECK_DIR = os.path.join(ROOT, "tests", "hostcheck")
+HOSTCHECK_LIB = os.path.join(HOSTCHECK_DIR, "libhostcheck.so")
+
+
+def build_hostcheck(force=False):
+    src = os.path.join(HOSTCHECK_DIR, "hostcheck.cpp")
+    csrc = os.path.join(ROOT, "era_zkevm_test_harness_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if force or not os.path.exists(HOSTCHECK_LIB) or any(os.path.getmtime(d) > os.path.getmtime(HOSTCHECK_LIB) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden", "-I/usr/local/cuda/include",
+                               "-o", HOSTCHECK_LIB, src])
+    return ctypes.CDLL(HOSTCHECK_LIB)
