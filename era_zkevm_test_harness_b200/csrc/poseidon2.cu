@@ -32,30 +32,26 @@ void poseidon2_permute_batch(Ctx* ctx, uint64_t* d_states, size_t n_states) {
     ctx->kernel_launches++;
 }
 
-// one thread per leaf; leaf i = for each column c: elems_per_leaf consecutive values at cols[c*stride + i*epl ..]
+// one thread per leaf; leaf i = for each column c: elems_per_leaf consecutive values at cols[c*stride + i*epl ..].
+// The sponge absorbs 8 elements per permutation (overwrite mode, zero padding of the last chunk); the loop is arranged so
+// the permutation has a single call site (code size, see poseidon2_core.cuh).
 __global__ void __launch_bounds__(128) leaf_hash_kernel(const uint64_t* __restrict__ cols, size_t col_stride, int n_cols, size_t n_leaves,
-                                                        int epl, uint64_t* __restrict__ digests) {
+                                                        int log_epl, uint64_t* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_leaves) return;
     uint64_t s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = 0;
-    int fill = 0;
-    for (int c = 0; c < n_cols; c++) {
-        const uint64_t* src = cols + (size_t)c * col_stride + i * (size_t)epl;
-        for (int e = 0; e < epl; e++) {
-            uint64_t v = src[e];
-            // s[fill] = v with a static-index switch so the state stays in registers
-            switch (fill) {
-                case 0: s[0] = v; break; case 1: s[1] = v; break; case 2: s[2] = v; break; case 3: s[3] = v; break;
-                case 4: s[4] = v; break; case 5: s[5] = v; break; case 6: s[6] = v; break; default: s[7] = v; break;
-            }
-            if (++fill == 8) { p2_permute(s); fill = 0; }
-        }
-    }
-    if (fill) {
+    const int leaf_len = n_cols << log_epl;
+    const int epl_mask = (1 << log_epl) - 1;
+    const uint64_t* base = cols + (i << log_epl);
+#pragma unroll 1
+    for (int e0 = 0; e0 < leaf_len; e0 += 8) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) if (k >= fill) s[k] = 0;
+        for (int k = 0; k < 8; k++) {
+            int e = e0 + k;
+            s[k] = e < leaf_len ? base[(size_t)(e >> log_epl) * col_stride + (e & epl_mask)] : 0;
+        }
         p2_permute(s);
     }
 #pragma unroll
@@ -79,8 +75,10 @@ void merkle_build(Ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t n_
                   size_t cap_size, uint64_t* d_tree) {
     ZK_REQUIRE(n_leaves && (n_leaves & (n_leaves - 1)) == 0, "merkle: n_leaves must be a power of two");
     ZK_REQUIRE(cap_size && (cap_size & (cap_size - 1)) == 0 && cap_size <= n_leaves, "merkle: bad cap size");
-    leaf_hash_kernel<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, (int)n_cols, n_leaves,
-                                                                                  (int)elems_per_leaf, d_tree);
+    ZK_REQUIRE(elems_per_leaf && (elems_per_leaf & (elems_per_leaf - 1)) == 0, "merkle: elems_per_leaf must be a power of two");
+    int log_epl = 0;
+    while (((size_t)1 << log_epl) < elems_per_leaf) log_epl++;
+    leaf_hash_kernel<<<(unsigned)((n_leaves + 127) / 128), 128, 0, ctx->stream>>>(d_cols, col_stride, (int)n_cols, n_leaves, log_epl, d_tree);
     CUDA_CHECK(cudaGetLastError());
     ctx->kernel_launches++;
     uint64_t* prev = d_tree;

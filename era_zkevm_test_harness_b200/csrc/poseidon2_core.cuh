@@ -50,27 +50,41 @@ GL_HD void p2x_internal(uint64_t (&s)[12]) {
     }
 }
 
+// One full round on 4 lanes at a time with the state rotated by 4 between iterations, so the S-box code (4 x 4
+// multiplies) exists ONCE in the instruction stream and is executed 3 times per round: the whole permutation is ~12 KB of
+// SASS instead of ~45 KB fully unrolled.  The hash kernels are instruction-fetch-bound otherwise (ncu: stall_no_instruction
+// dominated at 96 KB of code, profiles/r01_b_*).
+template <typename RC>
+GL_HD void p2x_full_round(uint64_t (&s)[12], const RC& rc, int r) {
+#pragma unroll 1
+    for (int it = 0; it < 3; it++) {
+        uint64_t n0 = glx::pow7(glx::add_canon(s[0], rc[12 * r + 4 * it]));
+        uint64_t n1 = glx::pow7(glx::add_canon(s[1], rc[12 * r + 4 * it + 1]));
+        uint64_t n2 = glx::pow7(glx::add_canon(s[2], rc[12 * r + 4 * it + 2]));
+        uint64_t n3 = glx::pow7(glx::add_canon(s[3], rc[12 * r + 4 * it + 3]));
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+        s[8] = n0; s[9] = n1; s[10] = n2; s[11] = n3;
+    }
+    p2x_external(s);
+}
+
 // in: any representatives; out: any representatives (canonicalise what you export)
 template <typename RC>
 GL_HD void p2x_permute(uint64_t (&s)[12], const RC& rc) {
     p2x_external(s);
     int r = 0;
 #pragma unroll 1
-    for (int k = 0; k < 4; k++, r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = glx::pow7(glx::add_canon(s[i], rc[12 * r + i]));
-        p2x_external(s);
-    }
+    for (int half = 0; half < 2; half++) {
 #pragma unroll 1
-    for (int k = 0; k < 22; k++, r++) {
-        s[0] = glx::pow7(glx::add_canon(s[0], rc[12 * r]));
-        p2x_internal(s);
-    }
+        for (int k = 0; k < 4; k++, r++) p2x_full_round(s, rc, r);
+        if (half == 0) {
 #pragma unroll 1
-    for (int k = 0; k < 4; k++, r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = glx::pow7(glx::add_canon(s[i], rc[12 * r + i]));
-        p2x_external(s);
+            for (int k = 0; k < 22; k++, r++) {
+                s[0] = glx::pow7(glx::add_canon(s[0], rc[12 * r]));
+                p2x_internal(s);
+            }
+        }
     }
 }
 
