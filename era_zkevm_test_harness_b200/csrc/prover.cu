@@ -13,6 +13,7 @@
 //   Merkle trees     [(2*leaves - cap)][4]
 #include <memory>
 #include "host_common.cuh"
+#include "quotient.cuh"
 
 namespace zk {
 
@@ -217,154 +218,7 @@ __global__ void scan_apply_kernel(const uint64_t* in0, const uint64_t* in1, size
     }
 }
 
-// ------------------------------------------------------------------------------------------------ quotient
-struct QuotParams {
-    zkgpu_geometry g;
-    const uint64_t* wit;    // coset evals, column stride cs_w, already offset to the coset
-    const uint64_t* setup;
-    const uint64_t* s2;
-    size_t cs_w, cs_s, cs_2;
-    const uint64_t* omega_br;  // w^bitrev(j)
-    const uint64_t* apow;      // alpha^k, interleaved (c0,c1)
-    const uint64_t* rc;        // Poseidon2 round constants (device copy)
-    uint64_t* t0;
-    uint64_t* t1;              // output, offset to the coset
-    uint32_t NP, C, E2, W, lookup_col0;
-    uint64_t shift, xn_minus_1, zh_inv, n_field;
-    gl::e2 beta, gamma, lbeta, lgamma;
-    uint64_t pi_values[ZKGPU_MAX_PUBLIC_INPUTS], pi_omega[ZKGPU_MAX_PUBLIC_INPUTS];
-};
-
-__global__ void __launch_bounds__(128) quotient_kernel(const __grid_constant__ QuotParams p) {
-    const uint32_t log_n = p.g.log_n;
-    const size_t N = (size_t)1 << log_n;
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    const zkgpu_geometry& g = p.g;
-    const uint64_t* w = p.wit + j;
-    const uint64_t* sg = p.setup + j;                                   // sigma columns
-    const uint64_t* kc = p.setup + (size_t)p.NP * p.cs_s + j;            // constant columns
-    const uint64_t* tb = kc + (size_t)g.n_const_cols * p.cs_s;           // table columns
-    const uint64_t* e2 = p.s2 + j;
-    const ulonglong2* apow = reinterpret_cast<const ulonglong2*>(p.apow);
-    const uint64_t x = gl::mul(p.shift, p.omega_br[j]);
-    gl::e2 acc = gl::make2(0, 0);
-    uint32_t k = 0;
-
-    // 1. gates
-    for (uint32_t gi = 0; gi < g.n_gates; gi++) {
-        const zkgpu_gate gt = g.gates[gi];
-        const uint32_t nrel = gate_relations(gt.kind) * gate_instances(gt, g.n_copy);
-        if (!nrel) continue;
-        uint64_t sel = 1;
-        for (uint32_t b = 0; b < gt.path_len; b++) {
-            uint64_t c = kc[(size_t)b * p.cs_s];
-            sel = gl::mul(sel, ((gt.path_bits >> b) & 1) ? c : gl::sub(1, c));
-        }
-        gl::e2 ga = gl::make2(0, 0);
-        uint32_t kk = k;
-        const uint64_t* gk = kc + (size_t)gt.path_len * p.cs_s;
-        eval_gate<uint64_t>(
-            gt, g.n_copy, p.rc, [&](uint32_t c) { return w[(size_t)c * p.cs_w]; }, [&](uint32_t i) { return gk[(size_t)i * p.cs_s]; },
-            [&](uint64_t r) {
-                ulonglong2 a = apow[kk++];
-                ga = gl::add(ga, gl::make2(gl::mul(a.x, r), gl::mul(a.y, r)));
-            });
-        acc = gl::add(acc, gl::mul_base(ga, sel));
-        k += nrel;
-    }
-    // 2. boolean column
-    if (g.has_boolean_col) {
-        uint64_t b = w[(size_t)g.n_copy * p.cs_w];
-        ulonglong2 a = apow[k++];
-        acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::sub(gl::sqr(b), b)));
-    }
-    // 3 + 5a. Lagrange denominators: N(x - w^row_i) for the public inputs and N(x - 1); one shared inversion
-    {
-        uint64_t den[ZKGPU_MAX_PUBLIC_INPUTS + 1], pre[ZKGPU_MAX_PUBLIC_INPUTS + 1];
-        const uint32_t nd = g.n_public_inputs + 1;
-        uint64_t run = 1;
-        for (uint32_t i = 0; i < nd; i++) {
-            uint64_t root = i < g.n_public_inputs ? p.pi_omega[i] : 1;
-            den[i] = gl::mul(p.n_field, gl::sub(x, root));
-            pre[i] = run;
-            run = gl::mul(run, den[i]);
-        }
-        uint64_t inv = gl::inv(run);
-        uint64_t l0_inv = 0;
-        for (int i = (int)nd - 1; i >= 0; i--) {
-            uint64_t di = gl::mul(inv, pre[i]);
-            inv = gl::mul(inv, den[i]);
-            if (i == (int)g.n_public_inputs) l0_inv = di;
-            else den[i] = di;  // reuse as inverse
-        }
-        for (uint32_t i = 0; i < g.n_public_inputs; i++) {
-            uint64_t lag = gl::mul(gl::mul(p.pi_omega[i], p.xn_minus_1), den[i]);
-            ulonglong2 a = apow[k++];
-            acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::mul(lag, gl::sub(w[(size_t)g.pi_col[i] * p.cs_w], p.pi_values[i]))));
-        }
-        // 4. lookup
-        if (g.lookup_reps) {
-            const uint32_t LW = g.lookup_width;
-            gl::e2 gp[9];
-            gp[0] = gl::make2(1, 0);
-            for (uint32_t q = 1; q <= LW; q++) gp[q] = gl::mul(gp[q - 1], p.lgamma);
-            gl::e2 tid = gl::mul_base(gp[LW], kc[(size_t)g.table_id_col * p.cs_s]);
-            for (uint32_t i = 0; i < g.lookup_reps; i++) {
-                gl::e2 den2 = gl::add(p.lbeta, tid);
-                for (uint32_t q = 0; q < LW; q++) den2 = gl::add(den2, gl::mul_base(gp[q], w[(size_t)(p.lookup_col0 + i * LW + q) * p.cs_w]));
-                gl::e2 A = gl::make2(e2[(size_t)(2 * (p.C + i)) * p.cs_2], e2[(size_t)(2 * (p.C + i) + 1) * p.cs_2]);
-                gl::e2 t = gl::mul(A, den2);
-                t.c0 = gl::sub(t.c0, 1);
-                ulonglong2 a = apow[k++];
-                acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
-            }
-            gl::e2 den2 = p.lbeta;
-            for (uint32_t q = 0; q <= LW; q++) den2 = gl::add(den2, gl::mul_base(gp[q], tb[(size_t)q * p.cs_s]));
-            gl::e2 B = gl::make2(e2[(size_t)(2 * (p.C + g.lookup_reps)) * p.cs_2], e2[(size_t)(2 * (p.C + g.lookup_reps) + 1) * p.cs_2]);
-            gl::e2 t = gl::mul(B, den2);
-            t.c0 = gl::sub(t.c0, w[(size_t)(p.W - 1) * p.cs_w]);
-            ulonglong2 a = apow[k++];
-            acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
-        }
-        // 5. copy permutation
-        gl::e2 zv = gl::make2(e2[0], e2[p.cs_2]);
-        {
-            uint64_t l0 = gl::mul(p.xn_minus_1, l0_inv);
-            gl::e2 t = gl::mul_base(gl::make2(gl::sub(zv.c0, 1), zv.c1), l0);
-            ulonglong2 a = apow[k++];
-            acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
-        }
-        // z(w*x): position of the next natural index inside the bit-reversed coset
-        const uint32_t nat = gl::bitrev((uint32_t)j, log_n);
-        const size_t jn = gl::bitrev((nat + 1) & (uint32_t)(N - 1), log_n);
-        const gl::e2 zs = gl::make2(p.s2[jn], p.s2[p.cs_2 + jn]);
-        uint64_t kx = x;
-        gl::e2 prev = zv;
-        for (uint32_t c = 0; c < p.C; c++) {
-            gl::e2 num = gl::make2(1, 0), dn = gl::make2(1, 0);
-            for (uint32_t i = c * g.quotient_degree; i < (c + 1) * g.quotient_degree && i < p.NP; i++) {
-                uint64_t wv = w[(size_t)i * p.cs_w];
-                gl::e2 a = gl::add(gl::mul_base(p.beta, kx), p.gamma);
-                a.c0 = gl::add(a.c0, wv);
-                gl::e2 b = gl::add(gl::mul_base(p.beta, sg[(size_t)i * p.cs_s]), p.gamma);
-                b.c0 = gl::add(b.c0, wv);
-                num = gl::mul(num, a);
-                dn = gl::mul(dn, b);
-                kx = gl::mul(kx, GL_GEN);
-            }
-            gl::e2 cur = (c + 1 < p.C) ? gl::make2(e2[(size_t)(2 * (c + 1)) * p.cs_2], e2[(size_t)(2 * (c + 1) + 1) * p.cs_2]) : zs;
-            gl::e2 t = gl::sub(gl::mul(cur, dn), gl::mul(prev, num));
-            ulonglong2 a = apow[k++];
-            acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
-            prev = cur;
-        }
-    }
-    acc = gl::mul_base(acc, p.zh_inv);
-    p.t0[j] = acc.c0;
-    p.t1[j] = acc.c1;
-}
-
+// ------------------------------------------------------------------------------------------------ quotient (kernels: quotient.cu)
 // coefficient i of the big-coset interpolation -> chunk monomials, undoing the shift 7^i
 __global__ void quotient_split_kernel(const uint64_t* t0, const uint64_t* t1, uint64_t* qmono, int log_n, size_t qn, uint64_t ginv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -645,14 +499,30 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.n_field = (uint64_t)N % GL_P;
         p.beta = beta; p.gamma = gamma; p.lbeta = lbeta; p.lgamma = lgamma;
         for (uint32_t i = 0; i < g.n_public_inputs; i++) { p.pi_values[i] = pi[i]; p.pi_omega[i] = gl::pow(gl::omega(log_n), g.pi_row[i]); }
+        {
+            uint32_t k = 0;
+            p.p2_gate = 0xFFFFFFFFu;
+            for (uint32_t gi = 0; gi < g.n_gates; gi++) {
+                p.gate_term0[gi] = k;
+                const uint32_t inst = gate_instances(g.gates[gi], g.n_copy);
+                if (inst && g.gates[gi].kind == ZKGPU_GATE_POSEIDON2_FLATTENED) {
+                    ZK_REQUIRE(p.p2_gate == 0xFFFFFFFFu, "prove: more than one flattened Poseidon2 gate");
+                    p.p2_gate = gi;
+                }
+                k += gate_relations(g.gates[gi].kind) * inst;
+            }
+            p.tail_term0 = k;
+            ZK_REQUIRE(g.lookup_width < 9, "prove: lookup width too large");
+            p.lgamma_pow[0] = gl::make2(1, 0);
+            for (uint32_t q = 1; q < 9; q++) p.lgamma_pow[q] = gl::mul(p.lgamma_pow[q - 1], lgamma);
+        }
         for (uint32_t c = 0; c < QD; c++) {
             p.wit = cos_w.p + (size_t)c * N; p.setup = st.cosets.p + (size_t)c * N; p.s2 = cos_2.p + (size_t)c * N;
             p.shift = lde_coset_shift(log_n, log_qd, c);
             p.xn_minus_1 = gl::sub(gl::pow(p.shift, N), 1);
             p.zh_inv = gl::inv(p.xn_minus_1);
             p.t0 = tq.p + (size_t)c * N; p.t1 = tq.p + QN + (size_t)c * N;
-            quotient_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(p);
-            LAUNCH_CHECK(ctx);
+            launch_quotient_coset(ctx, p);
         }
         // interpolate over the big coset: bit-reversed -> natural, inverse NTT (two columns), undo shift, split
         uint64_t* nat = tq.p + 2 * QN;

@@ -1,0 +1,419 @@
+// quotient.cu -- the quotient numerator over one coset of the 8N domain, as three compact kernels.
+//
+// Replaces the "compute quotient" stage of boojum's `prove_from_precomputations`
+// (/root/reference/src/prover_utils.rs:338-348); term order and relations are those of oracle/prover.c
+// `quotient_numerator` (gates in gate-list order, boolean column, public inputs, lookup, copy permutation).
+//
+// Why three kernels and why the loops are NOT unrolled: the first version (one kernel, everything inlined) was 286 KB of
+// SASS and ran at 1.4 IPC/SM with `stall_no_instruction` as the top stall (profiles/r01_b_prove_raw.csv) -- it was bound by
+// instruction fetch, not by arithmetic or HBM.  Here every hot loop body is a few KB:
+//   quotient_gates_kernel  general-purpose gates; instance loops stay rolled
+//   quotient_p2_kernel     the flattened Poseidon2 gate (118 relations of degree 7), 4 lanes per loop iteration
+//   quotient_perm_kernel   boolean column, public inputs, logUp lookup, copy-permutation chunks, division by Z_H
+// and the alpha-weighted sums  sum_k alpha^k * r_k  are accumulated UNREDUCED: a 64x64 product is four IMAD.WIDE.U32 into
+// three 96-bit column accumulators (1 fma + 1 alu instruction per partial product) and reduced mod p once per gate,
+// instead of two modular multiplies and two modular adds per relation.
+#include "host_common.cuh"
+#include "poseidon2_core.cuh"
+#include "quotient.cuh"
+
+namespace zk {
+
+// ------------------------------------------------------------------------------------------------ unreduced dot product
+// sum_k r_k * a_k over the integers: A0 + 2^32*A1 + 2^64*A2, each A_i a 96-bit (l, h, c) accumulator.
+struct Dot {
+    uint32_t l0, h0, c0, l1, h1, c1, l2, h2, c2;
+};
+__device__ __forceinline__ void dot_zero(Dot& d) { d.l0 = d.h0 = d.c0 = d.l1 = d.h1 = d.c1 = d.l2 = d.h2 = d.c2 = 0; }
+__device__ __forceinline__ void dot_add(Dot& d, uint64_t r, uint64_t a) {
+    uint32_t r0 = (uint32_t)r, r1 = (uint32_t)(r >> 32), a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32);
+    asm("mad.lo.cc.u32 %0, %9, %11, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %11, %1;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        "mad.lo.cc.u32 %3, %9, %12, %3;\n\t"
+        "madc.hi.cc.u32 %4, %9, %12, %4;\n\t"
+        "addc.u32 %5, %5, 0;\n\t"
+        "mad.lo.cc.u32 %3, %10, %11, %3;\n\t"
+        "madc.hi.cc.u32 %4, %10, %11, %4;\n\t"
+        "addc.u32 %5, %5, 0;\n\t"
+        "mad.lo.cc.u32 %6, %10, %12, %6;\n\t"
+        "madc.hi.cc.u32 %7, %10, %12, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(d.l0), "+r"(d.h0), "+r"(d.c0), "+r"(d.l1), "+r"(d.h1), "+r"(d.c1), "+r"(d.l2), "+r"(d.h2), "+r"(d.c2)
+        : "r"(r0), "r"(r1), "r"(a0), "r"(a1));
+}
+// value mod p, canonical.  limbs j0..j4 of the 160-bit total (before carry normalisation):
+//   j0 = l0, j1 = h0 + l1, j2 = c0 + h1 + l2, j3 = c1 + h2, j4 = c2
+// and 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod p)  =>  value = (j0 - j2 - j3) + 2^32 * (j1 + j2 - j4)
+__device__ __forceinline__ uint64_t dot_reduce(const Dot& d) {
+    int64_t j0 = d.l0, j1 = (int64_t)d.h0 + d.l1, j2 = (int64_t)d.c0 + d.h1 + d.l2, j3 = (int64_t)d.c1 + d.h2, j4 = d.c2;
+    int64_t lo = j0 - j2 - j3;   // |lo| < 2^35
+    int64_t hi = j1 + j2 - j4;   // |hi| < 2^35
+    // lo + 2^32*hi, made non-negative by adding 2^40 * p, then reduced as a 128-bit value
+    __int128 t = (__int128)lo + ((__int128)hi << 32) + ((__int128)GL_P << 40);
+    return gl::reduce128((uint64_t)t, (uint64_t)((unsigned __int128)t >> 64));
+}
+
+struct DotE2 {  // sum_k r_k * alpha_k for Ext2 weights
+    Dot a, b;
+};
+__device__ __forceinline__ void dote_zero(DotE2& d) { dot_zero(d.a); dot_zero(d.b); }
+__device__ __forceinline__ void dote_add(DotE2& d, uint64_t r, const ulonglong2 w) { dot_add(d.a, r, w.x); dot_add(d.b, r, w.y); }
+__device__ __forceinline__ gl::e2 dote_reduce(const DotE2& d) { return gl::make2(dot_reduce(d.a), dot_reduce(d.b)); }
+
+__device__ __forceinline__ uint64_t selector(const uint64_t* __restrict__ kc, size_t cs, uint32_t path_len, uint32_t path_bits) {
+    uint64_t sel = 1;
+    for (uint32_t b = 0; b < path_len; b++) {
+        uint64_t c = kc[(size_t)b * cs];
+        sel = gl::mul(sel, ((path_bits >> b) & 1) ? c : gl::sub(1, c));
+    }
+    return sel;
+}
+
+// ------------------------------------------------------------------------------------------------ general-purpose gates
+__global__ void __launch_bounds__(128) quotient_gates_kernel(const __grid_constant__ QuotParams p) {
+    const size_t N = (size_t)1 << p.g.log_n;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint64_t* __restrict__ w = p.wit + j;
+    const uint64_t* __restrict__ kc = p.setup + (size_t)p.NP * p.cs_s + j;
+    const ulonglong2* __restrict__ apow = reinterpret_cast<const ulonglong2*>(p.apow);
+    const size_t cw = p.cs_w, cs = p.cs_s;
+    gl::e2 acc = gl::make2(0, 0);
+
+#pragma unroll 1
+    for (uint32_t gi = 0; gi < p.g.n_gates; gi++) {
+        const zkgpu_gate gt = p.g.gates[gi];
+        const uint32_t inst = gate_instances(gt, p.g.n_copy);
+        if (!inst || gt.kind == ZKGPU_GATE_POSEIDON2_FLATTENED) continue;
+        const uint64_t* __restrict__ gk = kc + (size_t)gt.path_len * cs;
+        const ulonglong2* __restrict__ ap = apow + p.gate_term0[gi];
+        DotE2 d;
+        dote_zero(d);
+        switch (gt.kind) {
+            case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) dote_add(d, gl::sub(w[(size_t)t * cw], gk[(size_t)t * cs]), ap[t]);
+                break;
+            case ZKGPU_GATE_FMA: {
+                const uint64_t k0 = gk[0], k1 = gk[cs];
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(4 * t) * cw;
+                    uint64_t r = gl::sub(gl::add(gl::mul(gl::mul(k0, x[0]), x[cw]), gl::mul(k1, x[2 * cw])), x[3 * cw]);
+                    dote_add(d, r, ap[t]);
+                }
+            } break;
+            case ZKGPU_GATE_REDUCTION4: {
+                const uint64_t k0 = gk[0], k1 = gk[cs], k2 = gk[2 * cs], k3 = gk[3 * cs];
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(5 * t) * cw;
+                    uint64_t s = gl::add(gl::add(gl::mul(k0, x[0]), gl::mul(k1, x[cw])), gl::add(gl::mul(k2, x[2 * cw]), gl::mul(k3, x[3 * cw])));
+                    dote_add(d, gl::sub(s, x[4 * cw]), ap[t]);
+                }
+            } break;
+            case ZKGPU_GATE_SELECTION:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(4 * t) * cw;
+                    uint64_t b = x[2 * cw];
+                    // s*a + (1-s)*b - out = s*(a - b) + b - out
+                    dote_add(d, gl::sub(gl::add(gl::mul(x[0], gl::sub(x[cw], b)), b), x[3 * cw]), ap[t]);
+                }
+                break;
+            case ZKGPU_GATE_PARALLEL_SELECTION4:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(13 * t) * cw;
+                    const uint64_t s = x[0];
+#pragma unroll 1
+                    for (uint32_t i = 0; i < 4; i++) {
+                        const uint64_t* y = x + (size_t)(1 + 3 * i) * cw;
+                        uint64_t b = y[cw];
+                        dote_add(d, gl::sub(gl::add(gl::mul(s, gl::sub(y[0], b)), b), y[2 * cw]), ap[4 * t + i]);
+                    }
+                }
+                break;
+            case ZKGPU_GATE_ZERO_CHECK:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(3 * t) * cw;
+                    uint64_t xv = x[0], zf = x[2 * cw];
+                    dote_add(d, gl::sub(gl::mul(xv, x[cw]), gl::sub(1, zf)), ap[2 * t]);
+                    dote_add(d, gl::mul(xv, zf), ap[2 * t + 1]);
+                }
+                break;
+            case ZKGPU_GATE_UINTX_ADD: {
+                const uint64_t k0 = gk[0];
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(5 * t) * cw;
+                    uint64_t co = x[4 * cw];
+                    uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
+                    uint64_t rhs = gl::add(x[3 * cw], gl::mul(k0, co));
+                    dote_add(d, gl::sub(lhs, rhs), ap[2 * t]);
+                    dote_add(d, gl::sub(gl::sqr(co), co), ap[2 * t + 1]);
+                }
+            } break;
+            case ZKGPU_GATE_DOT_PRODUCT4:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(9 * t) * cw;
+                    uint64_t s = gl::add(gl::add(gl::mul(x[0], x[cw]), gl::mul(x[2 * cw], x[3 * cw])),
+                                         gl::add(gl::mul(x[4 * cw], x[5 * cw]), gl::mul(x[6 * cw], x[7 * cw])));
+                    dote_add(d, gl::sub(s, x[8 * cw]), ap[t]);
+                }
+                break;
+            case ZKGPU_GATE_U8X4_FMA:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(26 * t) * cw;
+                    // sum_{i,j} a_i b_j 2^(8(i+j)), grouped by i+j; then the linear part, byte position by byte position
+                    uint64_t a[4], b[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { a[i] = x[(size_t)i * cw]; b[i] = x[(size_t)(4 + i) * cw]; }
+                    uint64_t r = gl::mul(a[0], b[0]);
+#pragma unroll
+                    for (int s = 1; s < 7; s++) {
+                        uint64_t g = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            if (s - i >= 0 && s - i < 4) g = gl::add(g, gl::mul(a[i], b[s - i]));
+                        r = gl::add(r, gl::mul_pow2(g, 8 * s));
+                    }
+#pragma unroll 1
+                    for (uint32_t i = 0; i < 4; i++) {
+                        const uint64_t* y = x + (size_t)(8 + i) * cw;
+                        uint64_t lin = gl::sub(gl::add(y[0], y[4 * cw]), gl::add(y[8 * cw], gl::mul_pow2(y[12 * cw], 32)));
+                        r = gl::add(r, gl::mul_pow2(lin, 8 * i));
+                    }
+                    dote_add(d, r, ap[t]);
+                }
+                break;
+            case ZKGPU_GATE_FMA_EXT: {
+                const gl::e2 k0 = gl::make2(gk[0], gk[cs]), k1 = gl::make2(gk[2 * cs], gk[3 * cs]);
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(8 * t) * cw;
+                    gl::e2 ab = gl::mul(gl::make2(x[0], x[cw]), gl::make2(x[2 * cw], x[3 * cw]));
+                    gl::e2 r = gl::sub(gl::add(gl::mul(k0, ab), gl::mul(k1, gl::make2(x[4 * cw], x[5 * cw]))), gl::make2(x[6 * cw], x[7 * cw]));
+                    dote_add(d, r.c0, ap[2 * t]);
+                    dote_add(d, r.c1, ap[2 * t + 1]);
+                }
+            } break;
+            default: break;
+        }
+        const uint64_t sel = selector(kc, cs, gt.path_len, gt.path_bits);
+        acc = gl::add(acc, gl::mul_base(dote_reduce(d), sel));
+    }
+    p.t0[j] = acc.c0;
+    p.t1[j] = acc.c1;
+}
+
+// ------------------------------------------------------------------------------------------------ flattened Poseidon2 gate
+// columns: [0,12) input state, then one variable per S-box output in round order (48 + 22 + 48); relation k:
+//   v_k - (lin_k + rc_k)^7   where lin_k is the running linear-layer image of the previous variables.
+struct P2GateRC {
+    const uint64_t* rc;
+    __device__ __forceinline__ uint64_t operator[](int i) const { return rc[i]; }
+};
+__global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant__ QuotParams p) {
+    const size_t N = (size_t)1 << p.g.log_n;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint64_t* __restrict__ w = p.wit + j;
+    const uint64_t* __restrict__ kc = p.setup + (size_t)p.NP * p.cs_s + j;
+    const size_t cw = p.cs_w;
+    const zkgpu_gate gt = p.g.gates[p.p2_gate];
+    const ulonglong2* __restrict__ ap = reinterpret_cast<const ulonglong2*>(p.apow) + p.gate_term0[p.p2_gate];
+    const uint64_t* __restrict__ rc = p.rc;
+
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = w[(size_t)i * cw];
+    p2x_external(s);
+    DotE2 d;
+    dote_zero(d);
+    const uint64_t* __restrict__ v = w + (size_t)12 * cw;   // next variable column
+    int r = 0;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++, r++) {
+#pragma unroll 1
+            for (int it = 0; it < 3; it++) {
+                uint64_t nv[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    nv[u] = v[(size_t)u * cw];
+                    uint64_t rel = glx::sub(nv[u], glx::pow7(glx::add_canon(s[u], rc[12 * r + 4 * it + u])));
+                    dote_add(d, rel, ap[u]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) s[8 + u] = nv[u];
+                v += 4 * cw;
+                ap += 4;
+            }
+            p2x_external(s);
+        }
+        if (half == 0) {
+#pragma unroll 1
+            for (int q = 0; q < 22; q++, r++) {
+                uint64_t nv = v[0];
+                uint64_t rel = glx::sub(nv, glx::pow7(glx::add_canon(s[0], rc[12 * r])));
+                dote_add(d, rel, ap[0]);
+                s[0] = nv;
+                v += cw;
+                ap += 1;
+                p2x_internal(s);
+            }
+        }
+    }
+    const uint64_t sel = selector(kc, p.cs_s, gt.path_len, gt.path_bits);
+    gl::e2 acc = gl::mul_base(dote_reduce(d), sel);
+    p.t0[j] = gl::add(p.t0[j], acc.c0);
+    p.t1[j] = gl::add(p.t1[j], acc.c1);
+}
+
+// ------------------------------------------------------------------------------------------------ boolean, PI, lookup, copy permutation
+__device__ __forceinline__ uint64_t mul7(uint64_t x) { return gl::sub(gl::mul_pow2(x, 3), x); }
+
+__global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constant__ QuotParams p) {
+    const uint32_t log_n = p.g.log_n;
+    const size_t N = (size_t)1 << log_n;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const zkgpu_geometry& g = p.g;
+    const uint64_t* __restrict__ w = p.wit + j;
+    const uint64_t* __restrict__ sg = p.setup + j;
+    const uint64_t* __restrict__ kc = p.setup + (size_t)p.NP * p.cs_s + j;
+    const uint64_t* __restrict__ tb = kc + (size_t)g.n_const_cols * p.cs_s;
+    const uint64_t* __restrict__ e2 = p.s2 + j;
+    const ulonglong2* __restrict__ apow = reinterpret_cast<const ulonglong2*>(p.apow);
+    const size_t cw = p.cs_w, cs = p.cs_s, c2 = p.cs_2;
+    const uint64_t x = gl::mul(p.shift, p.omega_br[j]);
+    gl::e2 acc = gl::make2(p.t0[j], p.t1[j]);
+    uint32_t k = p.tail_term0;
+
+    // 2. boolean column
+    if (g.has_boolean_col) {
+        uint64_t b = w[(size_t)g.n_copy * cw];
+        ulonglong2 a = apow[k++];
+        acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::sub(gl::sqr(b), b)));
+    }
+    // 3 + 5a. Lagrange denominators N(x - w^row_i) for the public inputs and N(x - 1): one shared inversion
+    uint64_t l0_inv;
+    {
+        uint64_t den[ZKGPU_MAX_PUBLIC_INPUTS + 1], pre[ZKGPU_MAX_PUBLIC_INPUTS + 1];
+        const uint32_t nd = g.n_public_inputs + 1;
+        uint64_t run = 1;
+#pragma unroll 1
+        for (uint32_t i = 0; i < nd; i++) {
+            uint64_t root = i < g.n_public_inputs ? p.pi_omega[i] : 1;
+            den[i] = gl::mul(p.n_field, gl::sub(x, root));
+            pre[i] = run;
+            run = gl::mul(run, den[i]);
+        }
+        uint64_t inv = gl::inv(run);
+        l0_inv = 0;
+#pragma unroll 1
+        for (int i = (int)nd - 1; i >= 0; i--) {
+            uint64_t di = gl::mul(inv, pre[i]);
+            inv = gl::mul(inv, den[i]);
+            if (i == (int)g.n_public_inputs) l0_inv = di;
+            else den[i] = di;
+        }
+#pragma unroll 1
+        for (uint32_t i = 0; i < g.n_public_inputs; i++) {
+            uint64_t lag = gl::mul(gl::mul(p.pi_omega[i], p.xn_minus_1), den[i]);
+            ulonglong2 a = apow[k++];
+            acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::mul(lag, gl::sub(w[(size_t)g.pi_col[i] * cw], p.pi_values[i]))));
+        }
+    }
+    // 4. lookup
+    if (g.lookup_reps) {
+        const uint32_t LW = g.lookup_width;
+        const uint64_t* __restrict__ lw = w + (size_t)p.lookup_col0 * cw;
+        const gl::e2 tid = gl::mul_base(p.lgamma_pow[LW], kc[(size_t)g.table_id_col * cs]);
+#pragma unroll 1
+        for (uint32_t i = 0; i < g.lookup_reps; i++) {
+            gl::e2 den2 = gl::add(p.lbeta, tid);
+#pragma unroll 1
+            for (uint32_t q = 0; q < LW; q++) den2 = gl::add(den2, gl::mul_base(p.lgamma_pow[q], lw[(size_t)(i * LW + q) * cw]));
+            gl::e2 A = gl::make2(e2[(size_t)(2 * (p.C + i)) * c2], e2[(size_t)(2 * (p.C + i) + 1) * c2]);
+            gl::e2 t = gl::mul(A, den2);
+            t.c0 = gl::sub(t.c0, 1);
+            ulonglong2 a = apow[k++];
+            acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
+        }
+        gl::e2 den2 = p.lbeta;
+#pragma unroll 1
+        for (uint32_t q = 0; q <= LW; q++) den2 = gl::add(den2, gl::mul_base(p.lgamma_pow[q], tb[(size_t)q * cs]));
+        gl::e2 B = gl::make2(e2[(size_t)(2 * (p.C + g.lookup_reps)) * c2], e2[(size_t)(2 * (p.C + g.lookup_reps) + 1) * c2]);
+        gl::e2 t = gl::mul(B, den2);
+        t.c0 = gl::sub(t.c0, w[(size_t)(p.W - 1) * cw]);
+        ulonglong2 a = apow[k++];
+        acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
+    }
+    // 5. copy permutation
+    gl::e2 zv = gl::make2(e2[0], e2[c2]);
+    {
+        uint64_t l0 = gl::mul(p.xn_minus_1, l0_inv);
+        gl::e2 t = gl::mul_base(gl::make2(gl::sub(zv.c0, 1), zv.c1), l0);
+        ulonglong2 a = apow[k++];
+        acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
+    }
+    // z(w*x): position of the next natural index inside the bit-reversed coset
+    const uint32_t nat = gl::bitrev((uint32_t)j, log_n);
+    const size_t jn = gl::bitrev((nat + 1) & (uint32_t)(N - 1), log_n);
+    const gl::e2 zs = gl::make2(p.s2[jn], p.s2[c2 + jn]);
+    // a_i = w_i + beta*k_i*x + gamma with k_i = 7^i: keep u = beta*k_i*x + gamma - gamma and step it by a multiply-by-7
+    gl::e2 bkx = gl::mul_base(p.beta, x);
+    gl::e2 prev = zv;
+    const uint32_t QD = g.quotient_degree;
+#pragma unroll 1
+    for (uint32_t c = 0; c < p.C; c++) {
+        gl::e2 num = gl::make2(1, 0), dn = gl::make2(1, 0);
+        const uint32_t i1 = min((c + 1) * QD, p.NP);
+#pragma unroll 1
+        for (uint32_t i = c * QD; i < i1; i++) {
+            const uint64_t wv = w[(size_t)i * cw];
+            gl::e2 a = gl::add(bkx, p.gamma);
+            a.c0 = gl::add(a.c0, wv);
+            gl::e2 b = gl::add(gl::mul_base(p.beta, sg[(size_t)i * cs]), p.gamma);
+            b.c0 = gl::add(b.c0, wv);
+            num = gl::mul(num, a);
+            dn = gl::mul(dn, b);
+            bkx = gl::make2(mul7(bkx.c0), mul7(bkx.c1));
+        }
+        gl::e2 cur = (c + 1 < p.C) ? gl::make2(e2[(size_t)(2 * (c + 1)) * c2], e2[(size_t)(2 * (c + 1) + 1) * c2]) : zs;
+        gl::e2 t = gl::sub(gl::mul(cur, dn), gl::mul(prev, num));
+        ulonglong2 a = apow[k++];
+        acc = gl::add(acc, gl::mul(gl::make2(a.x, a.y), t));
+        prev = cur;
+    }
+    acc = gl::mul_base(acc, p.zh_inv);
+    p.t0[j] = acc.c0;
+    p.t1[j] = acc.c1;
+}
+
+void launch_quotient_coset(Ctx* ctx, const QuotParams& p) {
+    const size_t N = (size_t)1 << p.g.log_n;
+    const unsigned grid = (unsigned)((N + 127) / 128);
+    quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->kernel_launches++;
+    if (p.p2_gate != 0xFFFFFFFFu) {
+        quotient_p2_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->kernel_launches++;
+    }
+    quotient_perm_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->kernel_launches++;
+}
+
+}  // namespace zk
