@@ -93,6 +93,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->c.device);
     cudaStreamSynchronize(ctx->c.stream);
+    zk::ntt1024_forget(&ctx->c);
     for (void* p : ctx->c.persistent) cudaFree(p);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;

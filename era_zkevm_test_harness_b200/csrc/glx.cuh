@@ -137,3 +137,60 @@ GL_HD uint64_t pow7(uint64_t x) {
 }
 
 }  // namespace glx
+
+namespace glx {
+
+// lo + 2^64*hi mod p for ANY 64-bit hi (the tail of mul()); result in [0, 2^64), not canonical
+GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
+#ifdef __CUDA_ARCH__
+    uint32_t l0 = (uint32_t)lo, l1 = (uint32_t)(lo >> 32), h0 = (uint32_t)hi, h1 = (uint32_t)(hi >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 k,c;\n\t"
+        "sub.cc.u32 %2, %2, %5;\n\t"
+        "subc.cc.u32 %3, %3, 0;\n\t"
+        "subc.u32 k, 0, 0;\n\t"
+        "sub.cc.u32 %2, %2, k;\n\t"
+        "subc.u32 %3, %3, 0;\n\t"
+        "mad.lo.cc.u32 %2, %4, 0xffffffff, %2;\n\t"
+        "madc.hi.cc.u32 %3, %4, 0xffffffff, %3;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, c, 0xffffffff, %2;\n\t"
+        "madc.hi.u32 %1, c, 0xffffffff, %3;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1), "+r"(l0), "+r"(l1)
+        : "r"(h0), "r"(h1));
+    return ((uint64_t)r1 << 32) | r0;
+#else
+    uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+    uint64_t t = lo - hh;
+    if (lo < hh) t -= GL_EPS;
+    uint64_t m = hl * GL_EPS;
+    uint64_t r = t + m;
+    if (r < t) r += GL_EPS;
+    return r;
+#endif
+}
+
+// x * 2^S mod p for a compile-time 0 <= S < 96 and CANONICAL x; canonical result.  2 is a 192nd root of unity in
+// Goldilocks (2^96 = -1), so every twiddle of a 32-point (even 64-point) NTT is +-2^S: shifts instead of multiplies.
+template <int S>
+GL_HD uint64_t mul_2exp(uint64_t x) {
+    static_assert(S >= 0 && S < 96, "mul_2exp: exponent out of range");
+    if constexpr (S == 0) {
+        return x;
+    } else if constexpr (S <= 32) {
+        return canon(reduce96(x << S, (uint32_t)(x >> (64 - S))));
+    } else if constexpr (S < 64) {
+        return canon(reduce128(x << S, x >> (64 - S)));
+    } else {
+        // x*2^S = V*2^64 with V = x << (S-64) = vlo + 2^64*vhi:  vlo*2^64 + vhi*2^128 = hl*(2^32-1) - hh - vhi*2^32
+        constexpr int U = S - 64;
+        uint64_t vlo = x << U;
+        uint64_t vhi = U ? (x >> (64 - (U ? U : 1))) : 0;
+        uint64_t a = (uint64_t)(uint32_t)vlo * 0xFFFFFFFFull;   // <= (2^32-1)^2 < p
+        uint64_t b = (vlo >> 32) + (vhi << 32);                 // < 2^32 + 2^63 < p
+        return gl::sub(a, b);
+    }
+}
+
+}  // namespace glx

@@ -263,6 +263,7 @@ static void launch_pass(Ctx* ctx, NttPass p, int n_polys) {
 void ntt_forward_coset(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int log_n, int n_polys,
                        uint64_t shift) {
     if (n_polys == 0) return;
+    if (log_n == 20) { ntt1024_forward_coset(ctx, in, in_stride, out, out_stride, n_polys, shift); return; }
     const NttPlan& pl = get_ntt_plan(ctx, log_n, false);
     const CosetTables* ct = shift != 1 ? &get_coset_tables(ctx, log_n, shift) : nullptr;
     NttPass p{};
@@ -290,6 +291,7 @@ void ntt_forward_coset(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t*
 void ntt_inverse(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, uint64_t* tmp, size_t tmp_stride,
                  int log_n, int n_polys) {
     if (n_polys == 0) return;
+    if (log_n == 20) { ntt1024_inverse(ctx, in, in_stride, out, out_stride, tmp, tmp_stride, n_polys); return; }
     const NttPlan& pl = get_ntt_plan(ctx, log_n, true);
     NttPass p{};
     p.in = in; p.in_col_stride = in_stride;

@@ -73,6 +73,12 @@ inline uint64_t lde_coset_shift(int log_n, int log_lde, uint32_t c) {
     return gl::mul(GL_GEN, gl::pow(gl::omega(log_n + log_lde), gl::bitrev(c, log_lde)));
 }
 
+// ntt1024.cu -- the 2^20 fast path (two passes of 1024-point warp transforms)
+void ntt1024_forward_coset(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int n_polys, uint64_t shift);
+void ntt1024_inverse(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, uint64_t* tmp, size_t tmp_stride,
+                     int n_polys);
+void ntt1024_forget(Ctx* ctx);
+
 // poseidon2.cu
 void poseidon2_permute_batch(Ctx* ctx, uint64_t* d_states, size_t n_states);
 void merkle_build(Ctx* ctx, const uint64_t* d_cols, size_t col_stride, size_t n_cols, size_t n_leaves, size_t elems_per_leaf,

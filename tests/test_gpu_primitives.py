@@ -66,6 +66,30 @@ def test_ntt_full_size_roundtrip_and_spot_values(gpu, oracle):
     assert (lhs == oracle.vec("orc_gl_add_vec", two[0], two[1])).all()
 
 
+def test_ntt_2pow20_fast_path_inverse_inplace_and_lde(gpu, oracle):
+    """the 2^20 fast path (csrc/ntt1024.cu): inverse against the oracle bit for bit, forward in place == out of place,
+    and the LDE entry point (monomials + two cosets) against the oracle for a column with edge values."""
+    log_n, n = 20, 1 << 20
+    rng = np.random.default_rng(2020)
+    vals = rand_field(rng, (9, n))      # 9 columns: more members than one CTA tile row, odd batch
+    vals[0, :4] = [0, 1, P - 1, P - 2]
+    vals[1, :] = 0
+    vals[2, :] = P - 1
+    d_vals = to_device_u64(vals, gpu.device)
+    mono = gpu.ntt_inverse(d_vals, log_n)
+    mono_np = to_numpy_u64(mono)
+    for c in (0, 1, 2, 8):
+        assert (mono_np[c] == oracle.ntt(vals[c], inverse=True)).all(), c
+    ref = gpu.ntt_forward(mono, log_n, 7)
+    x = mono.clone()
+    gpu.ntt_forward(x, log_n, 7, out=x)
+    assert torch.equal(x, ref)
+    m2, lde = gpu.lde(d_vals[:3], log_n, 1)
+    o_mono, o_lde = oracle.lde(vals[:3], 1)
+    assert (to_numpy_u64(m2) == o_mono).all()
+    assert (to_numpy_u64(lde) == o_lde).all()
+
+
 @pytest.mark.parametrize("log_n,log_lde,n_cols", [(4, 1, 2), (10, 1, 9), (12, 3, 3), (13, 1, 4)])
 def test_lde_matches_oracle(gpu, oracle, log_n, log_lde, n_cols):
     rng = np.random.default_rng(log_n * 10 + log_lde)

@@ -63,3 +63,22 @@ def test_lazy_poseidon2_matches_oracle_permutation(hc, oracle):
     mine = st.copy()
     hc.hc_p2x_permute(mine.ctypes.data_as(vp), ctypes.c_size_t(len(mine)))
     assert (mine == ref).all()
+
+
+def test_mul_2exp_all_exponents(hc):
+    rng = np.random.default_rng(14)
+    a = rng.integers(0, P, size=2048, dtype=np.uint64)
+    a[:6] = [0, 1, P - 1, (1 << 32) - 1, 1 << 32, P - (1 << 32)]
+    out = np.empty_like(a)
+    for s in range(96):
+        assert hc.hc_glx_mul_2exp(a.ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(a.size), s) == 0
+        exp = np.array([(int(x) << s) % P for x in a], dtype=np.uint64)
+        assert (out == exp).all(), s
+
+
+def test_reduce128_any_hi(hc):
+    rng = np.random.default_rng(15)
+    lo, hi = _edge_mix(rng, 4096), _edge_mix(rng, 4096)[::-1].copy()
+    out = np.empty_like(lo)
+    hc.hc_glx_reduce128(lo.ctypes.data_as(vp), hi.ctypes.data_as(vp), out.ctypes.data_as(vp), ctypes.c_size_t(lo.size))
+    assert (out == np.array([(int(l) + (int(h) << 64)) % P for l, h in zip(lo, hi)], dtype=np.uint64)).all()
