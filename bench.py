@@ -175,17 +175,22 @@ def run_ours(args):
         PU.prove_circuit(ctx, sd, wit, proof_out=proof_np)   # pinned host witness -> H2D -> prove -> proof D2H
         gather_proofs()
 
+    per_step = []
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.kernel_launches
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
-        for _ in range(steps):
+        for i in range(steps):
             fn()
+            marks[i].record()
         e1.record()
         barrier()
+        per_step.append([round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(steps)])
         ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if distributed:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -268,7 +273,7 @@ def run_ours(args):
                        "proof_verified_by_cpu_verifier": verified},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit.nbytes), "d2h_bytes_per_step": n_proof * 8,
                     "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": extra,
+            "gpu_launches": launches, "ms_each_step": per_step, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": extra,
         }
         print(json.dumps(line))
     if distributed:

@@ -95,6 +95,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* ctx) {
     cudaStreamSynchronize(ctx->c.stream);
     zk::ntt1024_forget(&ctx->c);
     for (void* p : ctx->c.persistent) cudaFree(p);
+    if (ctx->c.arena_base) cudaFree(ctx->c.arena_base);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }

@@ -21,24 +21,72 @@ extern thread_local std::string g_last_error;
 void fri_fold(Ctx* ctx, const uint64_t* in0, const uint64_t* in1, int log_dom, uint64_t shift, gl::e2 ch, uint64_t* out0, uint64_t* out1);
 
 // ------------------------------------------------------------------------------------------------ device buffers
+// Scratch of one proof comes from the context's arena while an ArenaScope is open on this thread (bump allocation, freed
+// wholesale when the scope closes; a buffer released while it is the top of the stack gives its space back at once).
+// Outside a scope (setup creation) DevBuf falls back to the stream-ordered allocator.
+struct ArenaScope;
+static thread_local Ctx* g_arena_ctx = nullptr;
+
 struct DevBuf {
     uint64_t* p = nullptr;
     size_t n = 0;
     cudaStream_t stream = nullptr;
+    Ctx* arena = nullptr;
+    size_t arena_mark = 0;
     void alloc(size_t n_u64, cudaStream_t s) {
         release();
         stream = s;
         n = n_u64;
+        if (g_arena_ctx) {
+            Ctx* c = g_arena_ctx;
+            const size_t bytes = ((n_u64 ? n_u64 : 1) * 8 + 255) & ~(size_t)255;
+            if (c->arena_off + bytes > c->arena_cap)
+                throw Error(4, "prove: scratch arena exhausted (" + std::to_string(c->arena_cap >> 20) + " MiB)");
+            arena = c;
+            arena_mark = c->arena_off;
+            p = reinterpret_cast<uint64_t*>(c->arena_base + c->arena_off);
+            c->arena_off += bytes;
+            return;
+        }
         CUDA_CHECK(cudaMallocAsync((void**)&p, (n_u64 ? n_u64 : 1) * 8, s));
     }
     void release() {
-        if (p) cudaFreeAsync(p, stream);
+        if (p) {
+            if (arena) {
+                const size_t bytes = ((n ? n : 1) * 8 + 255) & ~(size_t)255;
+                if (arena->arena_off == arena_mark + bytes) arena->arena_off = arena_mark;   // top of the stack
+                arena = nullptr;
+            } else {
+                cudaFreeAsync(p, stream);
+            }
+        }
         p = nullptr;
     }
     ~DevBuf() { release(); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct ArenaScope {
+    Ctx* ctx;
+    bool owner;
+    ArenaScope(Ctx* c, size_t bytes) : ctx(c), owner(g_arena_ctx == nullptr) {
+        if (!owner) return;
+        if (c->arena_cap < bytes) {
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            if (c->arena_base) CUDA_CHECK(cudaFree(c->arena_base));
+            c->arena_base = nullptr;
+            c->arena_cap = 0;
+            CUDA_CHECK(cudaMalloc((void**)&c->arena_base, bytes));
+            c->arena_cap = bytes;
+        }
+        c->arena_off = 0;
+        g_arena_ctx = c;
+    }
+    ~ArenaScope() {
+        if (owner) g_arena_ctx = nullptr;
+    }
 };
 
 struct Setup {
@@ -392,12 +440,27 @@ static Setup* setup_create(Ctx* ctx, const zkgpu_geometry& g, const zkgpu_proof_
     return s.release();
 }
 
+// Host witness upload in column chunks on a second stream: chunk k's iNTT + coset NTTs run while chunk k+1 is still
+// crossing PCIe (zkgpu_prove).  ready[k] is recorded after columns [k*chunk, (k+1)*chunk) have landed.
+struct UploadPlan {
+    uint32_t chunk_cols = 0;
+    std::vector<cudaEvent_t> ready;
+};
+
 static void commit(Ctx* ctx, const Setup& st, const uint64_t* vals, uint32_t n_cols, DevBuf& mono, DevBuf& cosets, uint32_t n_cosets, DevBuf& tree,
-                   uint64_t* h_cap) {
+                   uint64_t* h_cap, const UploadPlan* plan = nullptr) {
     const Shape& sh = st.sh;
     mono.alloc((size_t)n_cols * sh.N, ctx->stream);
     cosets.alloc((size_t)n_cols * n_cosets * sh.N, ctx->stream);
     tree.alloc(merkle_tree_digests(sh.LN, st.cfg.cap_size) * 4, ctx->stream);
+    if (plan && plan->chunk_cols) {
+        for (size_t k = 0; k < plan->ready.size(); k++) {
+            const uint32_t c0 = (uint32_t)k * plan->chunk_cols, c1 = c0 + plan->chunk_cols < n_cols ? c0 + plan->chunk_cols : n_cols;
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, plan->ready[k], 0));
+            extend_columns(ctx, vals + (size_t)c0 * sh.N, mono.p + (size_t)c0 * sh.N, cosets.p + (size_t)c0 * n_cosets * sh.N, sh.log_n, n_cosets,
+                           c1 - c0);
+        }
+    } else
     extend_columns(ctx, vals, mono.p, cosets.p, sh.log_n, n_cosets, n_cols);
     merkle_build(ctx, cosets.p, (size_t)n_cosets * sh.N, n_cols, sh.LN, 1, st.cfg.cap_size, tree.p);
     d2h(ctx, h_cap, tree.p + 4 * merkle_cap_offset(sh.LN, st.cfg.cap_size), (size_t)st.cfg.cap_size * 32);
@@ -429,12 +492,23 @@ static void eval_columns(Ctx* ctx, const uint64_t* mono, size_t stride, uint32_t
     d2h(ctx, h_out, d_out, (size_t)n_cols * 16);
 }
 
-static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* proof, size_t capacity) {
+// upper bound of the scratch one proof takes from the arena (every buffer of prove(), no reuse assumed)
+static size_t prove_scratch_bytes(const Setup& st, bool with_witness_upload) {
+    const Shape& sh = st.sh;
+    const size_t N = sh.N, L = (size_t)1 << st.cfg.log_lde, E = st.E;
+    size_t words = (size_t)sh.W * (E + 1) * N + (size_t)sh.S2 * (E + 2) * N + 6 * (size_t)sh.QD * N + (size_t)sh.Q * (L + 1) * N + 8 * L * N;
+    words += 4 * merkle_tree_digests(sh.LN, st.cfg.cap_size) * 4 + 2 * L * N;   // oracle trees, FRI trees
+    if (with_witness_upload) words += (size_t)sh.W * N;
+    return words * 8 + ((size_t)64 << 20);
+}
+
+static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* proof, size_t capacity, const UploadPlan* plan = nullptr) {
     const zkgpu_geometry& g = st.g;
     const zkgpu_proof_config& cfg = st.cfg;
     const Shape& sh = st.sh;
     ZK_REQUIRE(capacity >= sh.proof_len, "prove: proof buffer too small");
     ZK_REQUIRE(st.device == ctx->device, "prove: setup lives on another device");
+    ArenaScope arena_scope(ctx, prove_scratch_bytes(st, false));
     const size_t N = sh.N, LN = sh.LN, cap = cfg.cap_size;
     const uint32_t W = sh.W, S = sh.S, S2 = sh.S2, Q = sh.Q, QD = sh.QD, E = st.E, L = 1u << cfg.log_lde;
     const int log_n = (int)g.log_n;
@@ -443,7 +517,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
 
     // ---- round 1: witness commitment
     DevBuf mono_w, cos_w, tree_w;
-    commit(ctx, st, d_wit, W, mono_w, cos_w, E, tree_w, cap_w.data());
+    commit(ctx, st, d_wit, W, mono_w, cos_w, E, tree_w, cap_w.data(), plan);
     std::vector<uint64_t> pi(g.n_public_inputs ? g.n_public_inputs : 1);
     for (uint32_t i = 0; i < g.n_public_inputs; i++)
         CUDA_CHECK(cudaMemcpyAsync(&pi[i], d_wit + (size_t)g.pi_col[i] * N + g.pi_row[i], 8, cudaMemcpyDeviceToHost, stream));
@@ -769,21 +843,44 @@ int zkgpu_prove_device(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* d_w
     }
 }
 int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_cols, uint64_t* h_proof_out, size_t proof_capacity_u64) {
+    cudaStream_t up = nullptr;
+    zk::UploadPlan plan;
+    cudaEvent_t allocated = nullptr;
+    int rc = 0;
     try {
         ZK_REQUIRE(ctx && s && s->s && h_witness_cols && h_proof_out, "prove: NULL argument");
         CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        zk::ArenaScope arena_scope(&ctx->c, zk::prove_scratch_bytes(*s->s, true));
         zk::DevBuf wit;
-        size_t n = (size_t)s->s->sh.W * s->s->sh.N;
-        wit.alloc(n, ctx->c.stream);
-        CUDA_CHECK(cudaMemcpyAsync(wit.p, h_witness_cols, n * 8, cudaMemcpyHostToDevice, ctx->c.stream));
-        zk::prove(&ctx->c, *s->s, wit.p, h_proof_out, proof_capacity_u64);
-        return 0;
+        const size_t N = s->s->sh.N;
+        const uint32_t W = s->s->sh.W;
+        wit.alloc((size_t)W * N, ctx->c.stream);
+        // upload in (up to) 8 column chunks on a side stream: the NTTs of chunk k overlap the PCIe transfer of chunk k+1
+        plan.chunk_cols = W >= 16 ? (W + 7) / 8 : W;
+        const uint32_t n_chunks = (W + plan.chunk_cols - 1) / plan.chunk_cols;
+        CUDA_CHECK(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&allocated, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventRecord(allocated, ctx->c.stream));
+        CUDA_CHECK(cudaStreamWaitEvent(up, allocated, 0));   // the stream-ordered allocation of `wit` comes first
+        for (uint32_t k = 0; k < n_chunks; k++) {
+            const uint32_t c0 = k * plan.chunk_cols, c1 = c0 + plan.chunk_cols < W ? c0 + plan.chunk_cols : W;
+            CUDA_CHECK(cudaMemcpyAsync(wit.p + (size_t)c0 * N, h_witness_cols + (size_t)c0 * N, (size_t)(c1 - c0) * N * 8, cudaMemcpyHostToDevice, up));
+            cudaEvent_t ev;
+            CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            plan.ready.push_back(ev);
+            CUDA_CHECK(cudaEventRecord(ev, up));
+        }
+        zk::prove(&ctx->c, *s->s, wit.p, h_proof_out, proof_capacity_u64, &plan);
     } catch (const zk::Error& e) {
         zk::g_last_error = e.what();
-        return e.code;
+        rc = e.code;
     } catch (const std::exception& e) {
         zk::g_last_error = e.what();
-        return 99;
+        rc = 99;
     }
+    if (up) { cudaStreamSynchronize(up); cudaStreamDestroy(up); }
+    for (cudaEvent_t e : plan.ready) cudaEventDestroy(e);
+    if (allocated) cudaEventDestroy(allocated);
+    return rc;
 }
 }

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ boolean, PI, lookup, copy permutation
-__device__ __forceinline__ uint64_t mul7(uint64_t x) { return gl::sub(gl::mul_pow2(x, 3), x); }
+__device__ __forceinline__ uint64_t mul7(uint64_t x) { return gl::sub(glx::mul_2exp<3>(x), x); }
 
 __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constant__ QuotParams p) {
     const uint32_t log_n = p.g.log_n;

@@ -53,6 +53,10 @@ struct Ctx {
     std::map<int, NttPlan> ntt_plans;
     std::map<std::pair<int, uint64_t>, CosetTables> coset_tables;
     uint64_t kernel_launches = 0;
+    // per-context scratch arena for one proof at a time (prover.cu): a bump allocator over one cudaMalloc'd block, so a proof
+    // performs no driver allocations at all once the arena has reached its size
+    char* arena_base = nullptr;
+    size_t arena_cap = 0, arena_off = 0;
 
     void* alloc_persistent(size_t bytes) {
         void* p = nullptr;
