@@ -155,7 +155,7 @@ def run_ours(args):
     n_proof = PU.proof_size_u64(geo, cfg)
     proof = torch.empty(n_proof, dtype=torch.int64).pin_memory()
     proof_np = proof.numpy().view(np.uint64)
-    gathered = [torch.empty(n_proof, dtype=torch.int64, device=dev) for _ in range(world)] if (distributed and rank == 0) else None
+    from era_zkevm_test_harness_b200 import farm
 
     def barrier():
         if distributed:
@@ -163,9 +163,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def gather_proofs():
+        # rank r proved instance r of this step; one NCCL gather of the fixed-size proof buffers to rank 0
         if distributed:
-            d_proof = proof.to(dev, non_blocking=True)
-            dist.gather(d_proof, gathered, dst=0)
+            return farm.gather_proofs({rank: proof_np}, n_proof, world, device=dev)
+        return [proof_np]
 
     def step_device():
         PU.prove_circuit(ctx, sd, d_wit, proof_out=proof_np)

@@ -26,6 +26,16 @@ __global__ void k(uint32_t* out, uint32_t seed) {
             if (OP == 6) { asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[i]) : "r"(b[i]));               // 1 imad : 1 add
                            asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(a[i])); }
             if (OP == 7) asm volatile("shf.l.wrap.b32 %0, %0, %1, 5;" : "+r"(a[i]) : "r"(b[i]));              // SHF
+            if (OP == 9) asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(b[i]));                       // IADD3.X alone
+            if (OP == 10) asm volatile("{.reg .pred q; setp.lt.u32 q, %0, %1; selp.u32 %0, %1, %0, q;}" : "+r"(a[i]) : "r"(b[i]));  // ISETP + SEL
+            if (OP == 11) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b[i]), "r"(seed));   // LOP3
+            if (OP == 12) asm volatile("prmt.b32 %0, %0, %1, 0x1032;" : "+r"(a[i]) : "r"(b[i]));              // PRMT
+            if (OP == 13) asm volatile("{.reg .pred q; setp.lt.u32 q, %0, %1; @q add.u32 %0, %0, %1;}" : "+r"(a[i]) : "r"(b[i]));   // ISETP + predicated IADD3
+            if (OP == 14) asm volatile("selp.u32 %0, %1, %0, %2;" : "+r"(a[i]) : "r"(b[i]), "r"((int)(it & 1)));  // hmm: setp+sel via int pred
+            if (OP == 15) asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.cc.u32 %1, %1, %3;\n\taddc.u32 %0, %0, 0;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // 3-chain
+            if (OP == 16) asm volatile("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // 64-bit sub
+            if (OP == 17) asm volatile("add.u64 %0, %0, %1;" : "+l"(w[i]) : "l"(((uint64_t)b[i] << 32) | a[i]));   // 64-bit add (compiler form)
+            if (OP == 18) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(a[i] ^ (uint32_t)w[i]), "r"(b[i]));  // IMAD.WIDE no addend (+xor)
             if (OP == 8) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // fused wide w/ carry
         }
     }
@@ -68,5 +78,14 @@ int main() {
     run<6>("1 IMAD + 1 add", 2);
     run<7>("SHF", 1);
     run<8>("mad.lo.cc+madc.hi (fused?)", 2);
+    run<9>("IADD3.X alone (addc)", 1);
+    run<10>("ISETP+SEL", 2);
+    run<11>("LOP3", 1);
+    run<12>("PRMT", 1);
+    run<13>("ISETP + @p IADD3", 2);
+    run<15>("add.cc+addc.cc+addc (3 chain)", 3);
+    run<16>("sub.cc+subc (64-bit sub)", 2);
+    run<17>("add.u64", 1);
+    run<18>("mul.wide + xor", 2);
     return 0;
 }
