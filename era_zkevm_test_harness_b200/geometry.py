@@ -255,3 +255,12 @@ def small_test_geometry(log_n=8, n_copy=16, lookup=True):
         g.gates[i].path_len = len(path)
         g.gates[i].path_bits = sum(int(b) << k for k, b in enumerate(path))
     return g
+
+
+def circuit_geometries_from_fixture(fixture):
+    """fixture: the dict of tests/golden/vk_shapes.json (tools/make_vk_fixtures.py).  Yields (key, Geometry, entry) for
+    the 13 base-layer circuits and the recursion-layer scheduler / leaf / node circuits of the reference."""
+    for t, entry in sorted(fixture["base"].items(), key=lambda kv: int(kv[0])):
+        yield f"base_{t}_{entry['variant']}", geometry_from_vk(entry, BASE_LAYER_GATE_ORDER[int(t)]), entry
+    for key, entry in fixture["recursion"].items():
+        yield f"recursion_{key}", geometry_from_vk(entry, RECURSION_GATE_ORDER), entry
