@@ -33,10 +33,11 @@ struct Ntt1024Params {
 template <bool IN_STRIDED, bool OUT_STRIDED, bool OUT_NATURAL, bool INVERSE>
 __global__ void __launch_bounds__(32 * NT_T, 2) ntt1024_kernel(const __grid_constant__ Ntt1024Params p) {
     constexpr int E32 = INVERSE ? NTT32_E_INV : NTT32_E_FWD;
-    extern __shared__ uint64_t smem[];
+    extern __shared__ __align__(128) uint64_t smem[];
+    __shared__ __align__(8) uint64_t bars[NT_T];   // one mbarrier per warp (pass B bulk loads)
     uint64_t* twid_s = smem;                 // 1024
     uint64_t* pre_s = smem + 1024;           // 32
-    uint64_t* data_all = smem + 1024 + 32;   // NT_T * NT_SP
+    uint64_t* data_all = smem + 1024 + 32;   // NT_T * NT_SP (member pitch 8480 B, 16-byte aligned)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t t0 = (size_t)blockIdx.x * NT_T;
     const size_t member = t0 + warp;
@@ -61,9 +62,33 @@ __global__ void __launch_bounds__(32 * NT_T, 2) ntt1024_kernel(const __grid_cons
         for (int b = 0; b < 32; b++) v[b] = data[33 * b + lane];
         __syncwarp();
     } else {
+        // the member's row is 8 KB contiguous: one TMA bulk copy (cp.async.bulk, SASS UBLKCP) per warp straight into the
+        // warp's exchange buffer, completion on a per-warp mbarrier; the 32 lanes then pick their stride-32 elements from
+        // shared memory (conflict-free).  Unaligned callers (row not 16-byte aligned) take plain coalesced loads.
         const uint64_t* row = in + (member << 10);
+        if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[warp]);
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(data);
+            if (lane == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 8192;" ::"r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 8192, [%2];"
+                             ::"r"(dst), "l"(row), "r"(bar) : "memory");
+            }
+            __syncwarp();
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                             : "=r"(done) : "r"(bar) : "memory");
+            }
 #pragma unroll
-        for (int b = 0; b < 32; b++) v[b] = row[32 * b + lane];
+            for (int b = 0; b < 32; b++) v[b] = data[32 * b + lane];
+            __syncwarp();
+        } else {
+#pragma unroll
+            for (int b = 0; b < 32; b++) v[b] = row[32 * b + lane];
+        }
         __syncthreads();   // twiddle table visible
     }
     if (p.pre != nullptr) {

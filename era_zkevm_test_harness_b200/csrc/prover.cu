@@ -14,6 +14,7 @@
 #include <memory>
 #include "host_common.cuh"
 #include "quotient.cuh"
+#include "dot.cuh"
 
 namespace zk {
 
@@ -294,11 +295,11 @@ __global__ void ext_pow_table_kernel(uint64_t* pw, size_t n, gl::e2 z) {
 __global__ void __launch_bounds__(256) eval_partial_kernel(const uint64_t* mono, size_t stride, size_t n, const uint64_t* pw, uint64_t* partial) {
     __shared__ uint64_t s0[256], s1[256];
     const uint64_t* m = mono + (size_t)blockIdx.y * stride;
-    gl::e2 acc = gl::make2(0, 0);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        uint64_t c = m[i];
-        acc = gl::add(acc, gl::make2(gl::mul(pw[i], c), gl::mul(pw[n + i], c)));
-    }
+    DotE2 d;   // sum_i c_i * z^i accumulated unreduced (dot.cuh): n / (gridDim.x * 256) <= 2^15 terms per thread
+    dote_zero(d);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dote_add(d, m[i], make_ulonglong2(pw[i], pw[n + i]));
+    const gl::e2 acc = dote_reduce(d);
     s0[threadIdx.x] = acc.c0; s1[threadIdx.x] = acc.c1;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -337,18 +338,14 @@ __global__ void __launch_bounds__(128) deep_kernel(const __grid_constant__ DeepP
     if (idx >> p.log_ln) return;
     const ulonglong2* phip = reinterpret_cast<const ulonglong2*>(p.phip);
     uint64_t x = gl::mul(GL_GEN, gl::pow(p.omega_ln, gl::bitrev((uint32_t)idx, p.log_ln)));
-    gl::e2 s = gl::make2(0, 0);
     uint32_t k = 0;
-    for (uint32_t i = 0; i < p.W; i++) {
-        ulonglong2 a = phip[k++];
-        uint64_t v = p.wit[(size_t)i * p.cs_w + idx];
-        s = gl::add(s, gl::make2(gl::mul(a.x, v), gl::mul(a.y, v)));
-    }
-    for (uint32_t i = 0; i < p.S; i++) {
-        ulonglong2 a = phip[k++];
-        uint64_t v = p.setup[(size_t)i * p.cs_s + idx];
-        s = gl::add(s, gl::make2(gl::mul(a.x, v), gl::mul(a.y, v)));
-    }
+    DotE2 d;   // sum_k phi^k * f_k(x) over the base-field columns, unreduced (dot.cuh)
+    dote_zero(d);
+#pragma unroll 4
+    for (uint32_t i = 0; i < p.W; i++) dote_add(d, p.wit[(size_t)i * p.cs_w + idx], phip[k++]);
+#pragma unroll 4
+    for (uint32_t i = 0; i < p.S; i++) dote_add(d, p.setup[(size_t)i * p.cs_s + idx], phip[k++]);
+    gl::e2 s = dote_reduce(d);
     for (uint32_t i = 0; i < p.E2; i++) {
         ulonglong2 a = phip[k++];
         s = gl::add(s, gl::mul(gl::make2(a.x, a.y), gl::make2(p.s2[(size_t)(2 * i) * p.cs_2 + idx], p.s2[(size_t)(2 * i + 1) * p.cs_2 + idx])));
