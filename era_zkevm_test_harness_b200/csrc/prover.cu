@@ -96,9 +96,22 @@ struct Setup {
     Shape sh;
     uint32_t E;            // cosets kept per column
     DevBuf vals, mono, cosets, tree;
+    DevBuf var_maps;       // optional: [NP][N] u32 variable index per copy-permutation cell (zkgpu_setup_set_variable_maps)
     std::vector<uint64_t> vk_cap;
     int device;
 };
+
+// ------------------------------------------------------------------------------------------------ witness materialisation
+// cols[c][r] = values[maps[c][r]] (0 for the placeholder): the step boojum performs from `vars_hint` at the top of
+// prove_from_precomputations.  One thread per cell; map reads and column writes are coalesced, the value reads are a gather
+// (the variable array of a 2^20 circuit is <= a few hundred MB, mostly L2 hits for the hot small-index variables).
+__global__ void materialize_columns_kernel(const uint32_t* __restrict__ maps, const uint64_t* __restrict__ values, size_t n_vars,
+                                           uint64_t* __restrict__ cols, size_t n_cells) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const uint32_t v = maps[i];
+    cols[i] = (v == ZKGPU_VAR_PLACEHOLDER || v >= n_vars) ? 0 : values[v];
+}
 
 // ------------------------------------------------------------------------------------------------ small kernels
 __global__ void omega_br_kernel(uint64_t* out, uint64_t omega, int log_n) {
@@ -879,5 +892,56 @@ int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_
     for (cudaEvent_t e : plan.ready) cudaEventDestroy(e);
     if (allocated) cudaEventDestroy(allocated);
     return rc;
+}
+
+int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_var_maps) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_var_maps, "set_variable_maps: NULL argument");
+        CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        zk::Setup& st = *s->s;
+        const size_t cells = (size_t)st.sh.NP * st.sh.N;
+        st.var_maps.alloc((cells + 1) / 2, ctx->c.stream);   // u32 cells in a u64 buffer
+        CUDA_CHECK(cudaMemcpyAsync(st.var_maps.p, h_var_maps, cells * 4, cudaMemcpyHostToDevice, ctx->c.stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
+}
+
+int zkgpu_prove_from_variables(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
+                               const uint64_t* h_multiplicities, uint64_t* h_proof_out, size_t proof_capacity_u64) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_variable_values && h_proof_out, "prove_from_variables: NULL argument");
+        CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        const zk::Setup& st = *s->s;
+        ZK_REQUIRE(st.var_maps.p != nullptr, "prove_from_variables: call zkgpu_setup_set_variable_maps first");
+        ZK_REQUIRE(n_vars < ZKGPU_VAR_PLACEHOLDER, "prove_from_variables: too many variables");
+        ZK_REQUIRE(st.g.lookup_reps == 0 || h_multiplicities != nullptr, "prove_from_variables: lookup circuit needs multiplicities");
+        const size_t N = st.sh.N, cells = (size_t)st.sh.NP * N;
+        zk::ArenaScope arena_scope(&ctx->c, zk::prove_scratch_bytes(st, true) + n_vars * 8);
+        zk::DevBuf wit, vals;
+        wit.alloc((size_t)st.sh.W * N, ctx->c.stream);
+        vals.alloc(n_vars ? n_vars : 1, ctx->c.stream);
+        CUDA_CHECK(cudaMemcpyAsync(vals.p, h_variable_values, n_vars * 8, cudaMemcpyHostToDevice, ctx->c.stream));
+        if (st.g.lookup_reps)
+            CUDA_CHECK(cudaMemcpyAsync(wit.p + cells, h_multiplicities, N * 8, cudaMemcpyHostToDevice, ctx->c.stream));
+        zk::materialize_columns_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->c.stream>>>(
+            reinterpret_cast<const uint32_t*>(st.var_maps.p), vals.p, n_vars, wit.p, cells);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->c.kernel_launches++;
+        zk::prove(&ctx->c, st, wit.p, h_proof_out, proof_capacity_u64);
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
 }
 }

@@ -92,6 +92,26 @@ def prove_circuit(ctx, setup: SetupData, witness_cols, proof_out=None):
     return proof
 
 
+def set_variable_maps(ctx, setup: SetupData, var_maps):
+    """var_maps: uint32 [n_perm, n] -- `DenseVariablesCopyHint` of the circuit type (row -> variable index per copy column,
+    0xFFFFFFFF = placeholder).  Uploaded once per setup; see prove_from_variables."""
+    m = np.ascontiguousarray(var_maps, dtype=np.uint32)
+    assert m.shape == (setup.geo.n_perm, 1 << setup.geo.log_n), m.shape
+    _lib.check(ctx.lib.zkgpu_setup_set_variable_maps(ctx.h, setup.handle, _p(m)))
+
+
+def prove_from_variables(ctx, setup: SetupData, variable_values, multiplicities=None, proof_out=None):
+    """The reference's hand-off (prove_from_precomputations(.., vars_hint, wits_hint, ..), src/prover_utils.rs:338-348): ship the
+    assembly's variable values (+ lookup multiplicities), gather the trace columns on the GPU, prove."""
+    n_u64 = proof_size_u64(setup.geo, setup.cfg)
+    proof = np.empty(n_u64, dtype=np.uint64) if proof_out is None else proof_out
+    v = np.ascontiguousarray(variable_values, dtype=np.uint64)
+    mp = None if multiplicities is None else np.ascontiguousarray(multiplicities, dtype=np.uint64)
+    _lib.check(ctx.lib.zkgpu_prove_from_variables(ctx.h, setup.handle, _p(v), v.size, _p(mp) if mp is not None else ctypes.c_void_p(0),
+                                                  _p(proof), n_u64))
+    return proof
+
+
 def verify_proof(geo: Geometry, cfg: ProofConfig, vk_cap, proof):
     """-> (bool, message).  CPU only, like the reference verifier."""
     lib = _lib.load()

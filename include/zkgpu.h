@@ -159,6 +159,19 @@ ZKGPU_API int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* 
 ZKGPU_API int zkgpu_prove_device(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* d_witness_cols, uint64_t* h_proof_out,
                                  size_t proof_capacity_u64);
 
+/* Witness hand-off as the reference does it: boojum's prove_from_precomputations takes `vars_hint: &DenseVariablesCopyHint`
+ * (src/prover_utils.rs:346) -- per copy-permutation column a dense map row -> variable index -- and materialises the trace
+ * columns itself from the assembly's variable values.  The maps are per circuit TYPE (part of the setup 7-tuple,
+ * src/prover_utils.rs:186-196), so they are uploaded once and stay resident; a proof then ships only the variable values.
+ *   h_var_maps: zkgpu_num_permuted_cols() x 2^log_n u32, column-major; entry = index into the variable-value array,
+ *               ZKGPU_VAR_PLACEHOLDER = unassigned cell (reads as 0, boojum's placeholder variable). */
+#define ZKGPU_VAR_PLACEHOLDER 0xFFFFFFFFu
+ZKGPU_API int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_var_maps);
+/* h_variable_values: n_vars canonical field elements; h_multiplicities: 2^log_n lookup multiplicities (NULL when the
+ * circuit has no lookup) -- boojum keeps them in the assembly next to the variable values.  GPU: gather -> columns -> prove. */
+ZKGPU_API int zkgpu_prove_from_variables(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
+                                         const uint64_t* h_multiplicities, uint64_t* h_proof_out, size_t proof_capacity_u64);
+
 /* Verifier::verify (src/prover_utils.rs:351-372): CPU only, as in the reference. Returns 0 iff the proof is valid,
  * 1 if invalid (message says which check failed), >1 on malformed input. */
 ZKGPU_API int zkgpu_verify(const zkgpu_geometry* g, const zkgpu_proof_config* cfg, const uint64_t* vk_cap, const uint64_t* proof,

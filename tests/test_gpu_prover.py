@@ -72,3 +72,49 @@ def test_full_size_mainvm_proof_verifies(gpu):
     ok, _ = PU.verify_proof(geo, cfg, sd.vk_cap, bad)
     assert not ok
     sd.close()
+
+
+def test_prove_from_variables_matches_column_path(gpu, oracle):
+    """the reference's hand-off: variable values + per-type variable maps (DenseVariablesCopyHint) instead of materialised
+    columns.  A random assignment of cells to variables (with repeated variables = copy constraints and placeholders for zero
+    cells) must give the same proof bytes as proving the columns directly."""
+    geo, cfg = CASES["mainvm_gates_2^9"]()
+    wit, setup = PU.synth_trace(geo, seed=17)
+    n, npm = 1 << geo.log_n, geo.n_perm
+    cells = wit[:npm].reshape(-1)
+    # variables = distinct cell values (equal cells share a variable, like copy-constrained cells do); zero cells -> placeholder
+    uniq, inverse = np.unique(cells, return_inverse=True)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(uniq.size)
+    values = np.empty_like(uniq)
+    values[perm] = uniq
+    maps = perm[inverse].astype(np.uint32)
+    maps[cells == 0] = np.uint32(0xFFFFFFFF)
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    PU.set_variable_maps(gpu, sd, maps.reshape(npm, n))
+    mult = wit[geo.n_witness - 1] if geo.lookup_reps else None
+    got = PU.prove_from_variables(gpu, sd, values, mult)
+    ref = PU.prove_circuit(gpu, sd, wit)
+    assert (got == ref).all()
+    assert (got == oracle.prove(geo, cfg, wit, setup)).all()
+    sd.close()
+
+
+def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
+    """compute_setups mirror: one VK JSON per circuit type under the reference's file names; the cap in each file is the
+    oracle's commitment of the same setup columns, the geometry read back from the file is the one that was committed."""
+    import json
+    import os
+    from era_zkevm_test_harness_b200 import compute_setups as CS
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
+    paths = CS.generate_base_layer_vks(gpu, str(tmp_path), fx, log_n=9)
+    paths.update(CS.generate_recursive_layer_vks(gpu, str(tmp_path), fx, log_n=9))
+    assert sorted(os.listdir(tmp_path / "base_layer")) == sorted(f"vk_{t}.json" for t in range(1, 14))
+    assert sorted(os.listdir(tmp_path / "recursion_layer")) == ["vk_1.json", "vk_3.json", "vk_node.json"]
+    for t in (1, 8, 10):
+        (variant, vk), = json.load(open(paths[t])).items()
+        assert variant == fx["base"][str(t)]["variant"] and vk["fixed_parameters"]["domain_size"] == 512
+        geo = G.geometry_from_vk(vk, G.BASE_LAYER_GATE_ORDER[t])
+        cfg = G.base_layer_proof_config(9)
+        setup = PU.synth_trace(geo, seed=0x5E7)[1]
+        assert (np.array(vk["setup_merkle_tree_cap"], dtype=np.uint64) == oracle.setup_cap(geo, cfg, setup)).all()
