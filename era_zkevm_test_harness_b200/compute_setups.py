@@ -44,7 +44,10 @@ def generate_circuit_setup_data(ctx, key, geo, entry, cfg=None, trace_source=_de
     setup_cols = trace_source(geo)
     sd = PU.create_setup_data(ctx, geo, cfg, setup_cols)
     fp = dict(entry["fixed_parameters"])
+    # a scaled-down trace (parity-test sizes) changes the size-dependent fields; at the reference's 2^20 these are no-ops
     fp["domain_size"] = 1 << geo.log_n
+    fp["total_tables_len"] = int(geo.table_len)
+    fp["public_inputs_locations"] = [[int(geo.pi_col[i]), int(geo.pi_row[i])] for i in range(geo.n_public_inputs)]
     return CircuitSetupData(key, entry["variant"], fp, sd)
 
 
