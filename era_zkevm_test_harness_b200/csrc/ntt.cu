@@ -213,19 +213,40 @@ const NttPlan& get_ntt_plan(Ctx* ctx, int log_n, bool inverse) {
     return ctx->ntt_plans.emplace(key, pl).first->second;
 }
 
+// Tables of shift^i for a coset.  The first MAX_CACHED_COSETS shifts of a size are cached (the LDE/quotient cosets of the
+// base and recursion layers: 8); beyond that (compression layers: LDE factor up to 2048) one transient table per size is
+// refilled on the stream before each transform -- no allocation and no synchronisation per coset.
+static constexpr size_t MAX_CACHED_COSETS = 16;
+static void fill_pow_table(Ctx* ctx, uint64_t* d, uint64_t base, size_t n) {
+    pow_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, base, 1, n);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->kernel_launches++;
+}
 const CosetTables& get_coset_tables(Ctx* ctx, int log_n, uint64_t shift) {
     auto key = std::make_pair(log_n, shift);
     auto it = ctx->coset_tables.find(key);
     if (it != ctx->coset_tables.end()) return it->second;
     const NttPlan& pl = get_ntt_plan(ctx, log_n, false);
-    CosetTables ct{};
-    if (pl.L2) {
-        ct.pre_e = make_pow_table(ctx, gl::pow(shift, (uint64_t)1 << pl.L2), 1, (size_t)1 << pl.L1);  // shift^(n2*i1)
-        ct.pre_t = make_pow_table(ctx, shift, 1, (size_t)1 << pl.L2);                                   // shift^i0
-    } else {
-        ct.pre_e = make_pow_table(ctx, shift, 1, (size_t)1 << pl.L1);
-        ct.pre_t = nullptr;
+    size_t cached = 0;
+    for (auto& kv : ctx->coset_tables) cached += kv.first.first == log_n;
+    const uint64_t base_e = pl.L2 ? gl::pow(shift, (uint64_t)1 << pl.L2) : shift;   // shift^(n2*i1), or shift^i for one pass
+    if (cached >= MAX_CACHED_COSETS) {
+        auto tkey = std::make_pair(log_n + 1000, (uint64_t)0);   // the transient slot of this size
+        auto tit = ctx->coset_tables.find(tkey);
+        if (tit == ctx->coset_tables.end()) {
+            CosetTables ct{};
+            ct.pre_e = (uint64_t*)ctx->alloc_persistent(((size_t)8) << pl.L1);
+            ct.pre_t = pl.L2 ? (uint64_t*)ctx->alloc_persistent(((size_t)8) << pl.L2) : nullptr;
+            tit = ctx->coset_tables.emplace(tkey, ct).first;
+        }
+        // stream order protects the previous transform that read the slot
+        fill_pow_table(ctx, tit->second.pre_e, base_e, (size_t)1 << pl.L1);
+        if (pl.L2) fill_pow_table(ctx, tit->second.pre_t, shift, (size_t)1 << pl.L2);
+        return tit->second;
     }
+    CosetTables ct{};
+    ct.pre_e = make_pow_table(ctx, base_e, 1, (size_t)1 << pl.L1);
+    ct.pre_t = pl.L2 ? make_pow_table(ctx, shift, 1, (size_t)1 << pl.L2) : nullptr;   // shift^i0
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return ctx->coset_tables.emplace(key, ct).first->second;
 }
@@ -248,10 +269,10 @@ static void launch_pass(Ctx* ctx, NttPass p, int n_polys) {
     int threads = thr_per * p.T;
     if (threads < 64) threads = 64;
     if (threads > 512) threads = 512;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // per device
+    if (!attr_set[ctx->device & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     dim3 grid((unsigned)((1u << p.LM) / p.T), (unsigned)n_polys);
     ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);

@@ -206,10 +206,10 @@ static const Ntt1024Tables::Coset& coset_tables(Ctx* ctx, uint64_t shift) {
 template <bool A, bool B, bool C, bool D>
 static void launch(Ctx* ctx, const Ntt1024Params& p, int n_polys) {
     constexpr size_t smem = (size_t)(1024 + 32 + NT_T * NT_SP) * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};   // the attribute is per device: one process may hold contexts on several GPUs
+    if (!attr_set[ctx->device & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(ntt1024_kernel<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_set[ctx->device & 63] = true;
     }
     // blockIdx.y is limited to 65535 polynomials per launch, far above any batch here
     dim3 grid(1024 / NT_T, (unsigned)n_polys);

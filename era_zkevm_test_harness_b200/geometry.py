@@ -147,6 +147,17 @@ def base_layer_proof_config(log_n=20):
 
 recursion_layer_proof_config = base_layer_proof_config  # lib.rs:39-47 -- same constants
 
+# aux_layer/compression_modes/mode_{1..4}.rs: (trace length, fri_lde_factor, merkle_tree_cap_size); security = L1_SECURITY_BITS = 80
+COMPRESSION_MODES = {1: (16, 32, 16), 2: (13, 512, 16), 3: (12, 1024, 16), 4: (15, 2048, 256)}
+
+
+def compression_layer_proof_config(mode, log_n=None):
+    """ProofConfig of CompressionMode{mode} (mode_N.rs `proof_config_for_compression_step`): queries 16 / 9 / 8 / 8.
+    The compression CIRCUITS (non-copied witness columns, ConditionalSwap / BoundedBoolean gates) are not restated yet;
+    the prover and verifier accept their proof configs (high LDE factors, cap 256) on any supported geometry."""
+    ln, lde, cap = COMPRESSION_MODES[mode]
+    return make_proof_config(ln if log_n is None else log_n, lde, cap, security_level=80)
+
 
 def _walk_selector_tree(node, path, out):
     """selectors_placement is {"Fork": {"left": .., "right": ..}} / {"GateOnly": {"gate_idx", "num_constants", "degree_of_gate", ..}} /

@@ -20,6 +20,8 @@ CASES = {
     "small_nolookup_lde4": lambda: (G.small_test_geometry(7, 20, False), G.make_proof_config(7, 4, 8, security_level=10)),
     "small_two_pass_ntt": lambda: (G.small_test_geometry(12, 16, True), G.make_proof_config(12, 2, 16, security_level=10)),
     "mainvm_gates_2^9": lambda: (G.mainvm_like_geometry(9), G.make_proof_config(9, 2, 16, security_level=8)),
+    "compression1_cfg_lde32": lambda: (G.small_test_geometry(9, 16, True), G.compression_layer_proof_config(1, 9)),
+    "compression4_cfg_lde2048_cap256": lambda: (G.small_test_geometry(6, 16, False), G.compression_layer_proof_config(4, 6)),
     "mainvm_gates_2^12": lambda: (G.mainvm_like_geometry(12), G.make_proof_config(12, 2, 16, security_level=20)),
 }
 

@@ -110,3 +110,17 @@ def test_mainvm_gate_set_small_trace(oracle, log_n):
     _, _, vk_cap, proof = _prove_small(oracle, geo, cfg, seed=5)
     ok, msg = PU.verify_proof(geo, cfg, vk_cap, proof)
     assert ok, msg
+
+
+@pytest.mark.parametrize("mode,queries", [(1, 16), (2, 9), (3, 8), (4, 8)])
+def test_compression_mode_proof_configs(oracle, mode, queries):
+    """proof configs of the compression chain (aux_layer/compression_modes/mode_N.rs): query counts as in the reference's
+    one-shot compression proofs (16/9/8/8), and the oracle prover + CPU verifier handle LDE 32..2048, cap 256"""
+    assert G.compression_layer_proof_config(mode).n_queries == queries
+    log_n = 6
+    geo = G.small_test_geometry(log_n, 16, lookup=(mode == 1))
+    cfg = G.compression_layer_proof_config(mode, log_n)
+    wit, setup = PU.synth_trace(geo, seed=mode)
+    proof = oracle.prove(geo, cfg, wit, setup)
+    ok, msg = PU.verify_proof(geo, cfg, oracle.setup_cap(geo, cfg, setup), proof)
+    assert ok, msg
