@@ -49,6 +49,7 @@ GL_HD uint32_t gate_width(uint32_t kind) {
         case ZKGPU_GATE_U8X4_FMA: return 26;
         case ZKGPU_GATE_POSEIDON2_FLATTENED: return 130;
         case ZKGPU_GATE_FMA_EXT: return 8;
+        case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 5;
         default: return 0;
     }
 }
@@ -65,6 +66,7 @@ GL_HD uint32_t gate_relations(uint32_t kind) {
         case ZKGPU_GATE_U8X4_FMA: return 1;
         case ZKGPU_GATE_POSEIDON2_FLATTENED: return 118;
         case ZKGPU_GATE_FMA_EXT: return 2;
+        case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 1;
         default: return 0;
     }
 }
@@ -173,6 +175,12 @@ GL_HD void eval_gate(const zkgpu_gate& g, uint32_t n_copy, const uint64_t* __res
                 sink(f_sub(f_mul(co, co), co));
             }
         } break;
+        case ZKGPU_GATE_U32_TRI_ADD_CARRY:
+            for (uint32_t t = 0; t < inst; t++) {
+                uint32_t b = 5 * t;
+                sink(f_sub(f_add(f_add(acc(b), acc(b + 1)), acc(b + 2)), f_add(acc(b + 3), f_shl(acc(b + 4), 32))));
+            }
+            break;
         case ZKGPU_GATE_DOT_PRODUCT4:
             for (uint32_t t = 0; t < inst; t++) {
                 uint32_t b = 9 * t;

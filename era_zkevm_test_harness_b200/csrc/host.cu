@@ -237,6 +237,14 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
                         x[3] = s & 0xFFFFFFFFULL; x[4] = s >> 32;
                     }
                     break;
+                case ZKGPU_GATE_U32_TRI_ADD_CARRY:
+                    for (uint32_t t = 0; t < inst; t++) {
+                        uint64_t* x = v.data() + 5 * t;
+                        for (int i = 0; i < 3; i++) x[i] = rng.next() & 0xFFFFFFFFULL;
+                        uint64_t s = x[0] + x[1] + x[2];
+                        x[3] = s & 0xFFFFFFFFULL; x[4] = s >> 32;  // carry in {0, 1, 2}
+                    }
+                    break;
                 case ZKGPU_GATE_DOT_PRODUCT4:
                     for (uint32_t t = 0; t < inst; t++) {
                         uint64_t* x = v.data() + 9 * t;

@@ -115,6 +115,14 @@ __global__ void __launch_bounds__(128) quotient_gates_kernel(const __grid_consta
                     dote_add(d, gl::sub(gl::sqr(co), co), ap[2 * t + 1]);
                 }
             } break;
+            case ZKGPU_GATE_U32_TRI_ADD_CARRY:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(5 * t) * cw;
+                    uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
+                    dote_add(d, gl::sub(lhs, gl::add(x[3 * cw], gl::mul_pow2(x[4 * cw], 32))), ap[t]);
+                }
+                break;
             case ZKGPU_GATE_DOT_PRODUCT4:
 #pragma unroll 1
                 for (uint32_t t = 0; t < inst; t++) {

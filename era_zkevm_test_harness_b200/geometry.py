@@ -17,14 +17,14 @@ MAX_FRI = 16
 
 # gate kinds (include/zkgpu.h)
 (GATE_NOP, GATE_CONSTANTS_ALLOCATOR, GATE_FMA, GATE_REDUCTION4, GATE_SELECTION, GATE_PARALLEL_SELECTION4, GATE_ZERO_CHECK,
- GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT) = range(12)
+ GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT, GATE_U32_TRI_ADD_CARRY) = range(13)
 
 GATE_NAMES = {
     "ConstantsAllocator": GATE_CONSTANTS_ALLOCATOR, "FmaBaseNoConst": GATE_FMA, "Reduction4": GATE_REDUCTION4,
     "Selection": GATE_SELECTION, "ParallelSelection4": GATE_PARALLEL_SELECTION4, "ZeroCheck": GATE_ZERO_CHECK,
     "UIntXAdd": GATE_UINTX_ADD, "DotProduct4": GATE_DOT_PRODUCT4, "U8x4FMA": GATE_U8X4_FMA,
     "Poseidon2Flattened": GATE_POSEIDON2_FLATTENED, "FmaExt": GATE_FMA_EXT, "PublicInput": GATE_NOP, "Nop": GATE_NOP,
-    "U32TriAddCarryAsChunk": GATE_NOP,  # StorageApplication only; relation not restated yet (DESIGN.md "Out of scope")
+    "U32TriAddCarryAsChunk": GATE_U32_TRI_ADD_CARRY,  # StorageApplication only
 }
 
 # gate_idx -> gate name per verification key, derived in SURVEY.md section 8a by matching each VK's

@@ -94,6 +94,7 @@ enum {
     ZKGPU_GATE_U8X4_FMA,              /* byte-decomposed a*b + c + carry = low + 2^32*high               U8x4FMAGate */
     ZKGPU_GATE_POSEIDON2_FLATTENED,   /* one whole Poseidon2 permutation per row, 118 relations of degree 7       */
     ZKGPU_GATE_FMA_EXT,               /* FMA over Ext2 (4 constants)                FmaGateInExtensionWithoutConstant */
+    ZKGPU_GATE_U32_TRI_ADD_CARRY,     /* a + b + c - out - 2^32*carry (carry range-checked as a lookup chunk)  U32TriAddCarryAsChunkGate */
     ZKGPU_GATE_KINDS
 };
 

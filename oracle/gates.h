@@ -9,11 +9,11 @@
 #include "gl64.h"
 
 static inline uint32_t og_width(uint32_t kind) {
-    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8};
+    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8, 5};
     return kind < ZKGPU_GATE_KINDS ? W[kind] : 0;
 }
 static inline uint32_t og_relations(uint32_t kind) {
-    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2};
+    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2, 1};
     return kind < ZKGPU_GATE_KINDS ? R[kind] : 0;
 }
 static inline uint32_t og_instances(const zkgpu_gate *g, uint32_t n_copy) {
@@ -101,6 +101,13 @@ static uint32_t og_eval_gate(const zkgpu_gate *g, uint32_t n_copy, const uint64_
             uint64_t rhs = gl_add(x[3], gl_mul(k[0], x[4]));
             out[n++] = gl_sub(lhs, rhs);
             out[n++] = gl_sub(gl_sqr(x[4]), x[4]);
+        }
+        break;
+    case ZKGPU_GATE_U32_TRI_ADD_CARRY: /* a + b + c = out + 2^32 * carry */
+        for (uint32_t t = 0; t < inst; t++) {
+            const uint64_t *x = v + 5 * t;
+            uint64_t rhs = gl_add(x[3], gl_mul(x[4], (uint64_t)1 << 32));
+            out[n++] = gl_sub(gl_add(gl_add(x[0], x[1]), x[2]), rhs);
         }
         break;
     case ZKGPU_GATE_DOT_PRODUCT4:
