@@ -39,6 +39,7 @@ SYMBOLS = {
     "zkgpu_prove_from_variables": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, sz, u64p, u64p, sz]),
     "zkgpu_verify": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
     "zkgpu_synth_trace": (ci, [ctypes.c_void_p, u64, u64p, u64p]),
+    "zkgpu_synth_trace_instance": (ci, [ctypes.c_void_p, u64, u64, u64p, u64p]),
 }
 
 _lib = None

@@ -50,6 +50,12 @@ GL_HD uint32_t gate_width(uint32_t kind) {
         case ZKGPU_GATE_POSEIDON2_FLATTENED: return 130;
         case ZKGPU_GATE_FMA_EXT: return 8;
         case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 5;
+        case ZKGPU_GATE_BOUNDED_BOOLEAN: return 1;
+        case ZKGPU_GATE_MATMUL12_EXTERNAL: return 24;
+        case ZKGPU_GATE_MATMUL12_INNER: return 24;
+        case ZKGPU_GATE_NONLINEARITY7: return 2;
+        case ZKGPU_GATE_CONDITIONAL_SWAP4: return 17;
+        case ZKGPU_GATE_ZERO_CHECK_WITNESS: return 2;   // x, flag under copy permutation; the inverse is a plain witness cell
         default: return 0;
     }
 }
@@ -67,18 +73,32 @@ GL_HD uint32_t gate_relations(uint32_t kind) {
         case ZKGPU_GATE_POSEIDON2_FLATTENED: return 118;
         case ZKGPU_GATE_FMA_EXT: return 2;
         case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 1;
+        case ZKGPU_GATE_BOUNDED_BOOLEAN: return 1;
+        case ZKGPU_GATE_MATMUL12_EXTERNAL: return 12;
+        case ZKGPU_GATE_MATMUL12_INNER: return 12;
+        case ZKGPU_GATE_NONLINEARITY7: return 1;
+        case ZKGPU_GATE_CONDITIONAL_SWAP4: return 8;
+        case ZKGPU_GATE_ZERO_CHECK_WITNESS: return 2;
         default: return 0;
     }
 }
-GL_HD uint32_t gate_instances(const zkgpu_gate& g, uint32_t n_copy) {
+// Gate CELLS: cell c < n_copy is copy column c; cell c >= n_copy is plain witness column c - n_copy (compression modes 1-3).
+// Only the flattened Poseidon2 gate spans both kinds of column (its 130 cells are the copy columns followed by the plain
+// witness columns: 52 + 78, 56 + 74, 68 + 62 in the reference's compression circuits); ZeroCheck-with-witness keeps x and the
+// flag under the copy permutation and puts instance t's inverse in plain witness cell t.
+constexpr uint32_t BOUNDED_BOOLEAN_MAX_ON_ROW = 10;  // mode_{2,3,4}.rs: BoundedBooleanConstraintGate::configure_builder(.., 10)
+GL_HD uint32_t gate_instances(const zkgpu_gate& g, const zkgpu_geometry& geo) {
     uint32_t w = gate_width(g.kind);
     if (!w) return 0;
     if (g.kind == ZKGPU_GATE_CONSTANTS_ALLOCATOR) return g.n_consts;
-    return n_copy / w;
+    if (g.kind == ZKGPU_GATE_POSEIDON2_FLATTENED) return (geo.n_copy + geo.n_witness_plain) / w;
+    if (g.kind == ZKGPU_GATE_BOUNDED_BOOLEAN) return geo.n_copy < BOUNDED_BOOLEAN_MAX_ON_ROW ? geo.n_copy : BOUNDED_BOOLEAN_MAX_ON_ROW;
+    if (g.kind == ZKGPU_GATE_ZERO_CHECK_WITNESS) return geo.n_copy / 2 < geo.n_witness_plain ? geo.n_copy / 2 : geo.n_witness_plain;
+    return geo.n_copy / w;
 }
 GL_HD uint32_t total_gate_terms(const zkgpu_geometry& geo) {
     uint32_t t = 0;
-    for (uint32_t i = 0; i < geo.n_gates; i++) t += gate_instances(geo.gates[i], geo.n_copy) * gate_relations(geo.gates[i].kind);
+    for (uint32_t i = 0; i < geo.n_gates; i++) t += gate_instances(geo.gates[i], geo) * gate_relations(geo.gates[i].kind);
     return t;
 }
 
@@ -115,13 +135,14 @@ GL_HD void p2g_internal(F (&s)[12]) {
 }
 
 // Evaluate every relation of one gate over its tiled instances.
-//   acc(v) : returns the value of copy column v at the current point (type F)
+//   acc(c) : returns the value of gate CELL c at the current point (type F); the caller maps cells to columns
 //   kc(i)  : returns gate constant i (constant column path_len + i) at the current point
 //   sink(r): receives each relation value in canonical order
 //   rc     : Poseidon2 round constant table (360 u64)
 template <typename F, typename Acc, typename Kc, typename Sink>
-GL_HD void eval_gate(const zkgpu_gate& g, uint32_t n_copy, const uint64_t* __restrict__ rc, Acc&& acc, Kc&& kc, Sink&& sink) {
-    const uint32_t inst = gate_instances(g, n_copy);
+GL_HD void eval_gate(const zkgpu_gate& g, const zkgpu_geometry& geo, const uint64_t* __restrict__ rc, Acc&& acc, Kc&& kc, Sink&& sink) {
+    const uint32_t inst = gate_instances(g, geo);
+    const uint32_t n_copy = geo.n_copy;
     switch (g.kind) {
         case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
             for (uint32_t t = 0; t < inst; t++) sink(f_sub(acc(t), kc(t)));
@@ -179,6 +200,46 @@ GL_HD void eval_gate(const zkgpu_gate& g, uint32_t n_copy, const uint64_t* __res
             for (uint32_t t = 0; t < inst; t++) {
                 uint32_t b = 5 * t;
                 sink(f_sub(f_add(f_add(acc(b), acc(b + 1)), acc(b + 2)), f_add(acc(b + 3), f_shl(acc(b + 4), 32))));
+            }
+            break;
+        case ZKGPU_GATE_BOUNDED_BOOLEAN:
+            for (uint32_t t = 0; t < inst; t++) {
+                F x = acc(t);
+                sink(f_sub(f_mul(x, x), x));
+            }
+            break;
+        case ZKGPU_GATE_MATMUL12_EXTERNAL:
+        case ZKGPU_GATE_MATMUL12_INNER:
+            for (uint32_t t = 0; t < inst; t++) {
+                uint32_t b = 24 * t;
+                F s[12];
+                for (int i = 0; i < 12; i++) s[i] = acc(b + i);
+                if (g.kind == ZKGPU_GATE_MATMUL12_EXTERNAL) p2g_external(s);
+                else p2g_internal(s);
+                for (int i = 0; i < 12; i++) sink(f_sub(acc(b + 12 + i), s[i]));
+            }
+            break;
+        case ZKGPU_GATE_NONLINEARITY7: {
+            F k0 = kc(0);
+            for (uint32_t t = 0; t < inst; t++) sink(f_sub(acc(2 * t + 1), f_pow7(f_add(acc(2 * t), k0))));
+        } break;
+        case ZKGPU_GATE_CONDITIONAL_SWAP4:
+            for (uint32_t t = 0; t < inst; t++) {
+                uint32_t b = 17 * t;   // a[4], b[4], should_swap, result_a[4], result_b[4]
+                F sw = acc(b + 8);
+                for (uint32_t i = 0; i < 4; i++) {
+                    F a = acc(b + i), bb = acc(b + 4 + i);
+                    F d = f_mul(sw, f_sub(bb, a));
+                    sink(f_sub(f_add(d, a), acc(b + 9 + i)));
+                    sink(f_sub(f_sub(bb, d), acc(b + 13 + i)));
+                }
+            }
+            break;
+        case ZKGPU_GATE_ZERO_CHECK_WITNESS:
+            for (uint32_t t = 0; t < inst; t++) {
+                F x = acc(2 * t), zf = acc(2 * t + 1), inv = acc(n_copy + t);
+                sink(f_sub(f_add(f_mul(x, inv), zf), f_one<F>()));
+                sink(f_mul(x, zf));
             }
             break;
         case ZKGPU_GATE_DOT_PRODUCT4:

@@ -45,6 +45,7 @@ void host_hash_node(const uint64_t* l, const uint64_t* r, uint64_t out[4]) {
 void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
     ZK_REQUIRE(g.log_n >= 4 && g.log_n <= 24, "geometry: log_n out of range [4,24]");
     ZK_REQUIRE(g.n_copy >= 1 && g.n_copy < 260, "geometry: n_copy out of range [1,260)");
+    ZK_REQUIRE(g.n_witness_plain < 260, "geometry: n_witness_plain out of range [0,260)");
     ZK_REQUIRE(g.quotient_degree >= 2 && g.quotient_degree <= 16 && (g.quotient_degree & (g.quotient_degree - 1)) == 0,
                "geometry: quotient_degree must be a power of two in [2,16]");
     ZK_REQUIRE(g.n_gates <= ZKGPU_MAX_GATES, "geometry: too many gates");
@@ -57,7 +58,9 @@ void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
         const zkgpu_gate& gt = g.gates[i];
         ZK_REQUIRE(gt.kind < ZKGPU_GATE_KINDS, "geometry: unknown gate kind");
         ZK_REQUIRE(gt.path_len + gt.n_consts <= g.n_const_cols, "geometry: gate selector path + constants exceed constant columns");
-        ZK_REQUIRE(gate_width(gt.kind) <= g.n_copy, "geometry: gate wider than the copy columns");
+        ZK_REQUIRE(gate_width(gt.kind) <= g.n_copy + (gt.kind == ZKGPU_GATE_POSEIDON2_FLATTENED ? g.n_witness_plain : 0),
+                   "geometry: gate wider than the columns it may use");
+        if (gt.kind == ZKGPU_GATE_NONLINEARITY7) ZK_REQUIRE(gt.n_consts >= 1, "geometry: nonlinearity gate needs 1 constant");
         if (gt.kind == ZKGPU_GATE_FMA) ZK_REQUIRE(gt.n_consts >= 2, "geometry: FMA gate needs 2 constants");
         if (gt.kind == ZKGPU_GATE_REDUCTION4 || gt.kind == ZKGPU_GATE_FMA_EXT) ZK_REQUIRE(gt.n_consts >= 4, "geometry: gate needs 4 constants");
         if (gt.kind == ZKGPU_GATE_UINTX_ADD) ZK_REQUIRE(gt.n_consts >= 1, "geometry: UIntXAdd gate needs 1 constant");
@@ -87,7 +90,8 @@ Shape make_shape(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
     s.QD = g.quotient_degree;
     s.NP = g.n_copy + (g.has_boolean_col ? 1 : 0) + g.lookup_width * g.lookup_reps;
     s.lookup_col0 = g.n_copy + (g.has_boolean_col ? 1 : 0);
-    s.W = s.NP + (g.lookup_reps ? 1 : 0);
+    s.plain_col0 = s.NP;
+    s.W = s.NP + g.n_witness_plain + (g.lookup_reps ? 1 : 0);
     s.S = s.NP + g.n_const_cols + (g.lookup_reps ? g.lookup_width + 1 : 0);
     s.C = (s.NP + s.QD - 1) / s.QD;
     s.E2 = s.C + g.lookup_reps + (g.lookup_reps ? 1 : 0);
@@ -136,7 +140,9 @@ static uint64_t table_entry(uint32_t t, uint32_t j, uint32_t width) {
     return m.next() & 0xFFFFFFFFULL;
 }
 
-static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, uint64_t* setup) {
+// setup_seed drives what a circuit TYPE fixes (gate constants); witness_seed drives the free witness values of one INSTANCE.
+// split = false keeps the original single-stream generator (zkgpu_synth_trace).
+static void synth_trace(const zkgpu_geometry& g, uint64_t setup_seed, uint64_t seed, bool split, uint64_t* wit, uint64_t* setup) {
     zkgpu_proof_config dummy{};
     dummy.log_lde = 1; dummy.cap_size = 1; dummy.n_queries = 1; dummy.n_fri_oracles = 1; dummy.fri_schedule[0] = 1;
     validate(g, dummy);
@@ -169,21 +175,24 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
     }
     std::vector<long> last_fma_row(1, -1);
     SplitMix rng{seed ^ 0xB2000000ULL};
-    std::vector<uint64_t> v(g.n_copy), kc(g.n_const_cols);
+    SplitMix rng_setup{setup_seed ^ 0x5E7000000ULL};
+    SplitMix& rk = split ? rng_setup : rng;
+    const uint32_t n_cells = g.n_copy + g.n_witness_plain;   // gate cells: copy columns, then plain witness columns
+    std::vector<uint64_t> v(n_cells), kc(g.n_const_cols);
     for (size_t r = 0; r < N; r++) {
-        for (uint32_t c = 0; c < g.n_copy; c++) v[c] = rng.field();
+        for (uint32_t c = 0; c < n_cells; c++) v[c] = rng.field();
         for (auto& x : kc) x = 0;
         const zkgpu_gate* gt = g.n_gates ? &g.gates[r % g.n_gates] : nullptr;
         if (gt) {
             for (uint32_t b = 0; b < gt->path_len; b++) kc[b] = (gt->path_bits >> b) & 1;
             uint64_t* k = kc.data() + gt->path_len;
-            const uint32_t inst = gate_instances(*gt, g.n_copy);
+            const uint32_t inst = gate_instances(*gt, g);
             switch (gt->kind) {
                 case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
-                    for (uint32_t t = 0; t < inst; t++) { k[t] = rng.field(); v[t] = k[t]; }
+                    for (uint32_t t = 0; t < inst; t++) { k[t] = rk.field(); v[t] = k[t]; }
                     break;
                 case ZKGPU_GATE_FMA: {
-                    k[0] = rng.field(); k[1] = rng.field();
+                    k[0] = rk.field(); k[1] = rk.field();
                     long prev = last_fma_row[0];
                     for (uint32_t t = 0; t < inst; t++) {
                         uint64_t* x = v.data() + 4 * t;
@@ -199,7 +208,7 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
                     last_fma_row[0] = (long)r;
                 } break;
                 case ZKGPU_GATE_REDUCTION4:
-                    for (int i = 0; i < 4; i++) k[i] = rng.field();
+                    for (int i = 0; i < 4; i++) k[i] = rk.field();
                     for (uint32_t t = 0; t < inst; t++) {
                         uint64_t* x = v.data() + 5 * t;
                         uint64_t s = 0;
@@ -245,6 +254,39 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
                         x[3] = s & 0xFFFFFFFFULL; x[4] = s >> 32;  // carry in {0, 1, 2}
                     }
                     break;
+                case ZKGPU_GATE_BOUNDED_BOOLEAN:
+                    for (uint32_t t = 0; t < inst; t++) v[t] = rng.next() & 1;
+                    break;
+                case ZKGPU_GATE_MATMUL12_EXTERNAL:
+                case ZKGPU_GATE_MATMUL12_INNER:
+                    for (uint32_t t = 0; t < inst; t++) {
+                        uint64_t* x = v.data() + 24 * t;
+                        uint64_t s[12];
+                        for (int i = 0; i < 12; i++) s[i] = x[i];
+                        if (gt->kind == ZKGPU_GATE_MATMUL12_EXTERNAL) p2g_external(s);
+                        else p2g_internal(s);
+                        for (int i = 0; i < 12; i++) x[12 + i] = s[i];
+                    }
+                    break;
+                case ZKGPU_GATE_NONLINEARITY7:
+                    k[0] = rk.field();
+                    for (uint32_t t = 0; t < inst; t++) v[2 * t + 1] = f_pow7(gl::add(v[2 * t], k[0]));
+                    break;
+                case ZKGPU_GATE_CONDITIONAL_SWAP4:
+                    for (uint32_t t = 0; t < inst; t++) {
+                        uint64_t* x = v.data() + 17 * t;
+                        x[8] = rng.next() & 1;
+                        for (int i = 0; i < 4; i++) { x[9 + i] = x[8] ? x[4 + i] : x[i]; x[13 + i] = x[8] ? x[i] : x[4 + i]; }
+                    }
+                    break;
+                case ZKGPU_GATE_ZERO_CHECK_WITNESS:
+                    for (uint32_t t = 0; t < inst; t++) {
+                        uint64_t* x = v.data() + 2 * t;
+                        uint64_t& inv = v[g.n_copy + t];
+                        if (rng.next() & 3) { inv = gl::inv(x[0] ? x[0] : (x[0] = 5)); x[1] = 0; }
+                        else { x[0] = 0; x[1] = 1; }
+                    }
+                    break;
                 case ZKGPU_GATE_DOT_PRODUCT4:
                     for (uint32_t t = 0; t < inst; t++) {
                         uint64_t* x = v.data() + 9 * t;
@@ -266,7 +308,7 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
                     }
                     break;
                 case ZKGPU_GATE_FMA_EXT:
-                    for (int i = 0; i < 4; i++) k[i] = rng.field();
+                    for (int i = 0; i < 4; i++) k[i] = rk.field();
                     for (uint32_t t = 0; t < inst; t++) {
                         uint64_t* x = v.data() + 8 * t;
                         gl::e2 d = gl::add(gl::mul(gl::make2(k[0], k[1]), gl::mul(gl::make2(x[0], x[1]), gl::make2(x[2], x[3]))),
@@ -302,6 +344,7 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t seed, uint64_t* wit, u
             }
         }
         for (uint32_t c = 0; c < g.n_copy; c++) wit[(size_t)c * N + r] = v[c];
+        for (uint32_t c = 0; c < g.n_witness_plain; c++) wit[(size_t)(sh.plain_col0 + c) * N + r] = v[g.n_copy + c];
         if (g.has_boolean_col) wit[(size_t)g.n_copy * N + r] = rng.next() & 1;
         if (g.lookup_reps) {
             kc[g.table_id_col] = 1;
@@ -398,11 +441,11 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
         gl::e2 acc = gl::make2(0, 0), ap = one;
         for (uint32_t gi = 0; gi < g.n_gates; gi++) {
             const zkgpu_gate& gt = g.gates[gi];
-            if (!gate_relations(gt.kind) || !gate_instances(gt, g.n_copy)) continue;
+            if (!gate_relations(gt.kind) || !gate_instances(gt, g)) continue;
             gl::e2 sel = one;
             for (uint32_t b = 0; b < gt.path_len; b++) sel = gl::mul(sel, ((gt.path_bits >> b) & 1) ? consts[b] : gl::sub(one, consts[b]));
             gl::e2 ga = gl::make2(0, 0);
-            eval_gate<gl::e2>(gt, g.n_copy, H_P2_RC, [&](uint32_t c) { return w[c]; }, [&](uint32_t i) { return consts[gt.path_len + i]; },
+            eval_gate<gl::e2>(gt, g, H_P2_RC, [&](uint32_t c) { return w[c < g.n_copy ? c : sh.plain_col0 + (c - g.n_copy)]; }, [&](uint32_t i) { return consts[gt.path_len + i]; },
                               [&](gl::e2 r) { ga = gl::add(ga, gl::mul(ap, r)); ap = gl::mul(ap, alpha); });
             acc = gl::add(acc, gl::mul(ga, sel));
         }
@@ -556,7 +599,17 @@ size_t zkgpu_proof_size_u64(const zkgpu_geometry* g, const zkgpu_proof_config* c
 }
 int zkgpu_synth_trace(const zkgpu_geometry* g, uint64_t seed, uint64_t* h_witness_cols, uint64_t* h_setup_cols) {
     try {
-        zk::synth_trace(*g, seed, h_witness_cols, h_setup_cols);
+        zk::synth_trace(*g, seed, seed, false, h_witness_cols, h_setup_cols);
+        return 0;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 1;
+    }
+}
+int zkgpu_synth_trace_instance(const zkgpu_geometry* g, uint64_t setup_seed, uint64_t witness_seed, uint64_t* h_witness_cols,
+                               uint64_t* h_setup_cols) {
+    try {
+        zk::synth_trace(*g, setup_seed, witness_seed, true, h_witness_cols, h_setup_cols);
         return 0;
     } catch (const std::exception& e) {
         zk::g_last_error = e.what();

@@ -26,6 +26,7 @@ struct Shape {
     size_t N, LN, depth;
     uint32_t log_n, log_lde, W, S, S2, Q, NP, C, E2, QD, n_at_z, n_at_zw, n_at_0, n_final, n_terms, NF;
     uint32_t lookup_col0;  // first lookup column inside the witness
+    uint32_t plain_col0;   // first plain (not copy-permuted) witness column = NP; gate cell c >= n_copy is column plain_col0 + c - n_copy
     size_t fri_dom_log[ZKGPU_MAX_FRI_ORACLES + 1], fri_leaves[ZKGPU_MAX_FRI_ORACLES], fri_cap[ZKGPU_MAX_FRI_ORACLES],
         fri_depth[ZKGPU_MAX_FRI_ORACLES];
     size_t proof_len;

@@ -588,7 +588,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
             p.p2_gate = 0xFFFFFFFFu;
             for (uint32_t gi = 0; gi < g.n_gates; gi++) {
                 p.gate_term0[gi] = k;
-                const uint32_t inst = gate_instances(g.gates[gi], g.n_copy);
+                const uint32_t inst = gate_instances(g.gates[gi], g);
                 if (inst && g.gates[gi].kind == ZKGPU_GATE_POSEIDON2_FLATTENED) {
                     ZK_REQUIRE(p.p2_gate == 0xFFFFFFFFu, "prove: more than one flattened Poseidon2 gate");
                     p.p2_gate = gi;
@@ -922,6 +922,8 @@ int zkgpu_prove_from_variables(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint6
         ZK_REQUIRE(st.var_maps.p != nullptr, "prove_from_variables: call zkgpu_setup_set_variable_maps first");
         ZK_REQUIRE(n_vars < ZKGPU_VAR_PLACEHOLDER, "prove_from_variables: too many variables");
         ZK_REQUIRE(st.g.lookup_reps == 0 || h_multiplicities != nullptr, "prove_from_variables: lookup circuit needs multiplicities");
+        ZK_REQUIRE(st.g.n_witness_plain == 0,
+                   "prove_from_variables: circuits with plain witness columns (compression modes 1-3) also need the witness hint; use zkgpu_prove");
         const size_t N = st.sh.N, cells = (size_t)st.sh.NP * N;
         zk::ArenaScope arena_scope(&ctx->c, zk::prove_scratch_bytes(st, true) + n_vars * 8);
         zk::DevBuf wit, vals;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) quotient_gates_kernel(const __grid_consta
 #pragma unroll 1
     for (uint32_t gi = 0; gi < p.g.n_gates; gi++) {
         const zkgpu_gate gt = p.g.gates[gi];
-        const uint32_t inst = gate_instances(gt, p.g.n_copy);
+        const uint32_t inst = gate_instances(gt, p.g);
         if (!inst || gt.kind == ZKGPU_GATE_POSEIDON2_FLATTENED) continue;
         const uint64_t* __restrict__ gk = kc + (size_t)gt.path_len * cs;
         const ulonglong2* __restrict__ ap = apow + p.gate_term0[gi];
@@ -123,6 +123,59 @@ __global__ void __launch_bounds__(128) quotient_gates_kernel(const __grid_consta
                     dote_add(d, gl::sub(lhs, gl::add(x[3 * cw], gl::mul_pow2(x[4 * cw], 32))), ap[t]);
                 }
                 break;
+            case ZKGPU_GATE_BOUNDED_BOOLEAN:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t x = w[(size_t)t * cw];
+                    dote_add(d, gl::sub(gl::sqr(x), x), ap[t]);
+                }
+                break;
+            case ZKGPU_GATE_MATMUL12_EXTERNAL:
+            case ZKGPU_GATE_MATMUL12_INNER:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(24 * t) * cw;
+                    uint64_t s[12];
+#pragma unroll
+                    for (int i = 0; i < 12; i++) s[i] = x[(size_t)i * cw];
+                    if (gt.kind == ZKGPU_GATE_MATMUL12_EXTERNAL) p2x_external(s);
+                    else p2x_internal(s);
+#pragma unroll
+                    for (int i = 0; i < 12; i++) dote_add(d, gl::sub(x[(size_t)(12 + i) * cw], glx::canon(s[i])), ap[12 * t + i]);
+                }
+                break;
+            case ZKGPU_GATE_NONLINEARITY7: {
+                const uint64_t k0 = gk[0];
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(2 * t) * cw;
+                    dote_add(d, gl::sub(x[cw], glx::canon(glx::pow7(glx::add_canon(x[0], k0)))), ap[t]);
+                }
+            } break;
+            case ZKGPU_GATE_CONDITIONAL_SWAP4:
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(17 * t) * cw;
+                    const uint64_t sw = x[8 * cw];
+#pragma unroll 1
+                    for (uint32_t i = 0; i < 4; i++) {
+                        const uint64_t a = x[(size_t)i * cw], b = x[(size_t)(4 + i) * cw];
+                        const uint64_t dl = gl::mul(sw, gl::sub(b, a));
+                        dote_add(d, gl::sub(gl::add(dl, a), x[(size_t)(9 + i) * cw]), ap[8 * t + 2 * i]);
+                        dote_add(d, gl::sub(gl::sub(b, dl), x[(size_t)(13 + i) * cw]), ap[8 * t + 2 * i + 1]);
+                    }
+                }
+                break;
+            case ZKGPU_GATE_ZERO_CHECK_WITNESS: {
+                const uint64_t* pw = w + (size_t)p.NP * cw;   // plain witness columns start at column NP
+#pragma unroll 1
+                for (uint32_t t = 0; t < inst; t++) {
+                    const uint64_t* x = w + (size_t)(2 * t) * cw;
+                    uint64_t xv = x[0], zf = x[cw];
+                    dote_add(d, gl::sub(gl::mul(xv, pw[(size_t)t * cw]), gl::sub(1, zf)), ap[2 * t]);
+                    dote_add(d, gl::mul(xv, zf), ap[2 * t + 1]);
+                }
+            } break;
             case ZKGPU_GATE_DOT_PRODUCT4:
 #pragma unroll 1
                 for (uint32_t t = 0; t < inst; t++) {
@@ -202,7 +255,10 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
     p2x_external(s);
     DotE2 d;
     dote_zero(d);
-    const uint64_t* __restrict__ v = w + (size_t)12 * cw;   // next variable column
+    // gate cell c: copy column c below n_copy, plain witness column NP + (c - n_copy) above (compression modes 1-3)
+    const uint32_t n_copy = p.g.n_copy, gap = p.NP - p.g.n_copy;
+    auto cell = [&](uint32_t c) -> uint64_t { return w[(size_t)(c < n_copy ? c : c + gap) * cw]; };
+    uint32_t v = 12;   // next variable cell
     int r = 0;
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
@@ -213,7 +269,7 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
                 uint64_t nv[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    nv[u] = v[(size_t)u * cw];
+                    nv[u] = cell(v + u);
                     uint64_t rel = glx::sub(nv[u], glx::pow7(glx::add_canon(s[u], rc[12 * r + 4 * it + u])));
                     dote_add(d, rel, ap[u]);
                 }
@@ -221,7 +277,7 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
                 for (int i = 0; i < 8; i++) s[i] = s[i + 4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) s[8 + u] = nv[u];
-                v += 4 * cw;
+                v += 4;
                 ap += 4;
             }
             p2x_external(s);
@@ -229,11 +285,11 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
         if (half == 0) {
 #pragma unroll 1
             for (int q = 0; q < 22; q++, r++) {
-                uint64_t nv = v[0];
+                uint64_t nv = cell(v);
                 uint64_t rel = glx::sub(nv, glx::pow7(glx::add_canon(s[0], rc[12 * r])));
                 dote_add(d, rel, ap[0]);
                 s[0] = nv;
-                v += cw;
+                v += 1;
                 ap += 1;
                 p2x_internal(s);
             }

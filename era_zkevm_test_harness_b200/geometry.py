@@ -17,7 +17,9 @@ MAX_FRI = 16
 
 # gate kinds (include/zkgpu.h)
 (GATE_NOP, GATE_CONSTANTS_ALLOCATOR, GATE_FMA, GATE_REDUCTION4, GATE_SELECTION, GATE_PARALLEL_SELECTION4, GATE_ZERO_CHECK,
- GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT, GATE_U32_TRI_ADD_CARRY) = range(13)
+ GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT, GATE_U32_TRI_ADD_CARRY,
+ GATE_BOUNDED_BOOLEAN, GATE_MATMUL12_EXTERNAL, GATE_MATMUL12_INNER, GATE_NONLINEARITY7, GATE_CONDITIONAL_SWAP4,
+ GATE_ZERO_CHECK_WITNESS) = range(19)
 
 GATE_NAMES = {
     "ConstantsAllocator": GATE_CONSTANTS_ALLOCATOR, "FmaBaseNoConst": GATE_FMA, "Reduction4": GATE_REDUCTION4,
@@ -25,6 +27,9 @@ GATE_NAMES = {
     "UIntXAdd": GATE_UINTX_ADD, "DotProduct4": GATE_DOT_PRODUCT4, "U8x4FMA": GATE_U8X4_FMA,
     "Poseidon2Flattened": GATE_POSEIDON2_FLATTENED, "FmaExt": GATE_FMA_EXT, "PublicInput": GATE_NOP, "Nop": GATE_NOP,
     "U32TriAddCarryAsChunk": GATE_U32_TRI_ADD_CARRY,  # StorageApplication only
+    # compression circuits (aux_layer/compression_modes/mode_{1..4}.rs)
+    "BoundedBoolean": GATE_BOUNDED_BOOLEAN, "MatMul12External": GATE_MATMUL12_EXTERNAL, "MatMul12Inner": GATE_MATMUL12_INNER,
+    "Nonlinearity7": GATE_NONLINEARITY7, "ConditionalSwap4": GATE_CONDITIONAL_SWAP4, "ZeroCheckWitness": GATE_ZERO_CHECK_WITNESS,
 }
 
 # gate_idx -> gate name per verification key, derived in SURVEY.md section 8a by matching each VK's
@@ -46,6 +51,17 @@ for _t in (3, 6):
 for _t in (5, 13):
     BASE_LAYER_GATE_ORDER[_t] = ["ConstantsAllocator", "ZeroCheck", "FmaBaseNoConst", "UIntXAdd", "Selection", "ParallelSelection4",
                                  "PublicInput", "Reduction4"]
+# compression_{N}_vk.json: gate_idx follows the configure_builder order of mode_N.rs; (num_constants, degree) per gate_idx
+# match the VKs: Poseidon2Flattened (0, 7), MatMul12 (0, 1) x 2, Nonlinearity7 (1, 7), ConditionalSwap4 (0, 2), ...
+_COMPRESSION_TAIL = ["FmaBaseNoConst", "FmaExt", "Selection", "ParallelSelection4", "ConditionalSwap4", "PublicInput", "Reduction4"]
+COMPRESSION_GATE_ORDER = {
+    # mode 1: BooleanConstraintGate sits in its own specialised column (has_boolean_col), ZeroCheck keeps its inverse in a witness column
+    1: ["ConstantsAllocator", "Poseidon2Flattened", "ZeroCheckWitness"] + _COMPRESSION_TAIL,
+    2: ["ConstantsAllocator", "BoundedBoolean", "Poseidon2Flattened", "ZeroCheckWitness"] + _COMPRESSION_TAIL,
+    3: ["ConstantsAllocator", "BoundedBoolean", "Poseidon2Flattened", "ZeroCheckWitness"] + _COMPRESSION_TAIL,
+    # mode 4: no plain witness columns; the round function is built from matrix-multiplication and x^7 gates (48 columns < 130)
+    4: ["ConstantsAllocator", "BoundedBoolean", "MatMul12External", "MatMul12Inner", "Nonlinearity7", "ZeroCheck"] + _COMPRESSION_TAIL,
+}
 RECURSION_GATE_ORDER = ["ConstantsAllocator", "Poseidon2Flattened", "ZeroCheck", "FmaBaseNoConst", "FmaExt", "UIntXAdd", "Selection",
                         "ParallelSelection4", "PublicInput", "Reduction4"]
 
@@ -61,7 +77,7 @@ class Gate(ctypes.Structure):
 
 
 class Geometry(ctypes.Structure):
-    _fields_ = [("log_n", ctypes.c_uint32), ("n_copy", ctypes.c_uint32), ("n_const_cols", ctypes.c_uint32),
+    _fields_ = [("log_n", ctypes.c_uint32), ("n_copy", ctypes.c_uint32), ("n_witness_plain", ctypes.c_uint32), ("n_const_cols", ctypes.c_uint32),
                 ("lookup_width", ctypes.c_uint32), ("lookup_reps", ctypes.c_uint32), ("table_id_col", ctypes.c_uint32),
                 ("has_boolean_col", ctypes.c_uint32), ("quotient_degree", ctypes.c_uint32), ("table_len", ctypes.c_uint32),
                 ("n_public_inputs", ctypes.c_uint32), ("pi_col", ctypes.c_uint32 * MAX_PI), ("pi_row", ctypes.c_uint32 * MAX_PI),
@@ -73,8 +89,8 @@ class Geometry(ctypes.Structure):
         return self.n_copy + (1 if self.has_boolean_col else 0) + self.lookup_width * self.lookup_reps
 
     @property
-    def n_witness(self):
-        return self.n_perm + (1 if self.lookup_reps else 0)
+    def n_witness(self):  # copy-permuted columns, plain witness columns, lookup multiplicities
+        return self.n_perm + self.n_witness_plain + (1 if self.lookup_reps else 0)
 
     @property
     def n_setup(self):
@@ -105,22 +121,23 @@ class ProofConfig(ctypes.Structure):
                 ("n_fri_oracles", ctypes.c_uint32), ("fri_schedule", ctypes.c_uint32 * MAX_FRI)]
 
 
-def fri_schedule(log_n, log_lde, cap_size, final_log_degree=3):
-    """Folding schedule as the golden proofs show it: fold by 8 while the next oracle still has at
-    least cap_size leaves, close with a smaller fold, stop at a final polynomial of 2^final_log_degree coefficients.
-    2^20, lde 2, cap 16 -> [3,3,3,3,3,2]."""
-    total = max(log_n - final_log_degree, 1)
-    log_dom = log_n + log_lde
+def fri_schedule(log_n, log_lde, cap_size):
+    """Folding schedule as the golden proofs show it: fold by 8 while (a) the new oracle still has at least cap_size leaves
+    and (b) the polynomial still has degree bits left; the last oracle folds by less, and what is left is the final
+    polynomial.  2^20, lde 2, cap 16 -> [3,3,3,3,3,2] + 8 final monomials (base/recursion goldens); 2^20, cap 32 ->
+    [3,3,3,3,3,1] (proof.json); compression modes: 2^16 lde 32 -> [3,3,3,3,3,1], 2^13 lde 512 -> [3,3,3,3,1],
+    2^12 lde 1024 -> [3,3,3,3], 2^15 lde 2048 cap 256 -> [3,3,3,3,3], all with ONE final monomial
+    (compression_{1..4}_proof.json)."""
+    log_dom, deg_bits, log_cap = log_n + log_lde, log_n, int(math.log2(cap_size))
     sched = []
-    while total > 0:
-        s = min(3, total)
-        # an oracle over 2^log_dom points with leaves of 2^s points needs >= cap_size leaves
-        while s > 1 and (1 << (log_dom - s)) < cap_size:
-            s -= 1
+    while True:
+        s = min(3, deg_bits, log_dom - log_cap)
+        if s <= 0:
+            break
         sched.append(s)
-        total -= s
+        deg_bits -= s
         log_dom -= s
-    return sched
+    return sched or [1]
 
 
 def make_proof_config(log_n, fri_lde_factor=2, merkle_tree_cap_size=16, security_level=100, pow_bits=0, schedule=None):
@@ -153,8 +170,8 @@ COMPRESSION_MODES = {1: (16, 32, 16), 2: (13, 512, 16), 3: (12, 1024, 16), 4: (1
 
 def compression_layer_proof_config(mode, log_n=None):
     """ProofConfig of CompressionMode{mode} (mode_N.rs `proof_config_for_compression_step`): queries 16 / 9 / 8 / 8.
-    The compression CIRCUITS (non-copied witness columns, ConditionalSwap / BoundedBoolean gates) are not restated yet;
-    the prover and verifier accept their proof configs (high LDE factors, cap 256) on any supported geometry."""
+    The circuits themselves (plain witness columns, BoundedBoolean / ConditionalSwap / matrix-multiplication gates) come from
+    the compression VKs: compression_geometries_from_fixture."""
     ln, lde, cap = COMPRESSION_MODES[mode]
     return make_proof_config(ln if log_n is None else log_n, lde, cap, security_level=80)
 
@@ -173,7 +190,7 @@ def _walk_selector_tree(node, path, out):
     out.append((g["gate_idx"], g["num_constants"], g.get("degree_of_gate", g.get("degree")), list(path)))
 
 
-def geometry_from_vk(vk, gate_order):
+def geometry_from_vk(vk, gate_order, has_boolean_col=1):
     """vk: the inner dict of a VK JSON file ({"fixed_parameters": .., "setup_merkle_tree_cap": ..});
     gate_order: gate names by gate_idx (BASE_LAYER_GATE_ORDER[type] / RECURSION_GATE_ORDER)."""
     fp = vk["fixed_parameters"]
@@ -181,7 +198,7 @@ def geometry_from_vk(vk, gate_order):
     g = Geometry()
     g.log_n = int(math.log2(fp["domain_size"]))
     g.n_copy = par["num_columns_under_copy_permutation"]
-    assert par["num_witness_columns"] == 0, "non-copied witness columns are not used by any reference circuit"
+    g.n_witness_plain = par["num_witness_columns"]  # compression modes 1-3 only
     lp = fp["lookup_parameters"]
     if lp == "NoLookup":
         g.lookup_width = g.lookup_reps = 0
@@ -191,7 +208,9 @@ def geometry_from_vk(vk, gate_order):
         g.lookup_width, g.lookup_reps = body["width"], body["num_repetitions"]
     g.n_const_cols = par["num_constant_columns"] + fp["extra_constant_polys_for_selectors"] + (1 if g.lookup_reps else 0)
     g.table_id_col = fp["table_ids_column_idxes"][0] if g.lookup_reps else 0
-    g.has_boolean_col = 1 if g.lookup_reps or True else 0  # every reference circuit places BooleanConstraintGate in its own column
+    # every base/recursion circuit (and compression mode 1) places BooleanConstraintGate in its own specialised column;
+    # compression modes 2-4 use BoundedBooleanConstraintGate on general-purpose columns instead
+    g.has_boolean_col = has_boolean_col
     g.quotient_degree = fp["quotient_degree"]
     g.table_len = fp["total_tables_len"]
     pis = fp["public_inputs_locations"]
@@ -275,3 +294,15 @@ def circuit_geometries_from_fixture(fixture):
         yield f"base_{t}_{entry['variant']}", geometry_from_vk(entry, BASE_LAYER_GATE_ORDER[int(t)]), entry
     for key, entry in fixture["recursion"].items():
         yield f"recursion_{key}", geometry_from_vk(entry, RECURSION_GATE_ORDER), entry
+
+
+def compression_geometries_from_fixture(fixture):
+    """(key, Geometry, ProofConfig, entry) for the compression-layer circuits of the fixture: modes 1-4 as the one-shot
+    compression_{N}_vk.json describe them, plus the wrapper-facing variants (same circuits, their own proof configs)."""
+    for key, entry in fixture.get("compression", {}).items():
+        mode = entry["mode"]
+        geo = geometry_from_vk(entry, COMPRESSION_GATE_ORDER[mode], has_boolean_col=1 if mode == 1 else 0)
+        fp = entry["fixed_parameters"]
+        sec = entry["proof_shapes"][0]["proof_config"]["security_level"] if entry.get("proof_shapes") else 80
+        cfg = make_proof_config(geo.log_n, fp["fri_lde_factor"], fp["cap_size"], security_level=sec)
+        yield f"compression_{key}", geo, cfg, entry

@@ -34,8 +34,9 @@ def proof_size_u64(geo, cfg):
     return int(n)
 
 
-def synth_trace(geo, seed=0, pinned=False):
-    """Synthetic satisfying trace (stands in for Rust synthesis): returns (witness_cols [W,n], setup_cols [S,n]) uint64."""
+def synth_trace(geo, seed=0, pinned=False, witness_seed=None):
+    """Synthetic satisfying trace (stands in for Rust synthesis): returns (witness_cols [W,n], setup_cols [S,n]) uint64.
+    With `witness_seed`, `seed` fixes the circuit type (setup columns) and `witness_seed` the instance (witness columns)."""
     lib = _lib.load()
     n = 1 << geo.log_n
     if pinned:
@@ -46,7 +47,10 @@ def synth_trace(geo, seed=0, pinned=False):
     else:
         wit = np.empty((geo.n_witness, n), dtype=np.uint64)
         setup = np.empty((geo.n_setup, n), dtype=np.uint64)
-    _lib.check(lib.zkgpu_synth_trace(ctypes.byref(geo), seed, _p(wit), _p(setup)))
+    if witness_seed is None:
+        _lib.check(lib.zkgpu_synth_trace(ctypes.byref(geo), seed, _p(wit), _p(setup)))
+    else:
+        _lib.check(lib.zkgpu_synth_trace_instance(ctypes.byref(geo), seed, witness_seed, _p(wit), _p(setup)))
     return wit, setup
 
 

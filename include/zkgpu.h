@@ -95,6 +95,12 @@ enum {
     ZKGPU_GATE_POSEIDON2_FLATTENED,   /* one whole Poseidon2 permutation per row, 118 relations of degree 7       */
     ZKGPU_GATE_FMA_EXT,               /* FMA over Ext2 (4 constants)                FmaGateInExtensionWithoutConstant */
     ZKGPU_GATE_U32_TRI_ADD_CARRY,     /* a + b + c - out - 2^32*carry (carry range-checked as a lookup chunk)  U32TriAddCarryAsChunkGate */
+    ZKGPU_GATE_BOUNDED_BOOLEAN,       /* x^2 - x on the first min(10, n_copy) copy columns (deg 2)         BoundedBooleanConstraintGate */
+    ZKGPU_GATE_MATMUL12_EXTERNAL,     /* out_i - sum_j M_E[i][j] in_j, 12 relations (deg 1)  MatrixMultiplicationGate<12, Poseidon2 external> */
+    ZKGPU_GATE_MATMUL12_INNER,        /* out_i - sum_j M_I[i][j] in_j, 12 relations (deg 1)  MatrixMultiplicationGate<12, Poseidon2 inner>    */
+    ZKGPU_GATE_NONLINEARITY7,         /* y - (x + k)^7, one gate constant (deg 7)                         SimpleNonlinearityGate<7> */
+    ZKGPU_GATE_CONDITIONAL_SWAP4,     /* s*(b_i-a_i)+a_i-ra_i, s*(a_i-b_i)+b_i-rb_i, i<4 (deg 2)             ConditionalSwapGate<4> */
+    ZKGPU_GATE_ZERO_CHECK_WITNESS,    /* ZeroCheckGate with the inverse in a plain witness column (use_witness = true)        */
     ZKGPU_GATE_KINDS
 };
 
@@ -113,6 +119,9 @@ typedef struct {
 typedef struct {
     uint32_t log_n;             /* domain_size = 2^log_n                                                           */
     uint32_t n_copy;            /* parameters.num_columns_under_copy_permutation                                    */
+    uint32_t n_witness_plain;   /* parameters.num_witness_columns: witness columns NOT under the copy permutation
+                                 * (compression modes 1-3: 78 / 74 / 62).  Gate cells [n_copy, n_copy + n_witness_plain)
+                                 * live there: the flattened Poseidon2 gate's 130 cells span both kinds of column.     */
     uint32_t n_const_cols;      /* num_constant_columns + extra_constant_polys_for_selectors (+1 table-id column)   */
     uint32_t lookup_width;      /* lookup_parameters width (0 = no lookup)                                          */
     uint32_t lookup_reps;       /* num_repetitions                                                                  */
@@ -137,7 +146,7 @@ typedef struct {
 } zkgpu_proof_config;
 
 /* derived column counts (identical formulas in prover, verifier and oracle) */
-ZKGPU_API uint32_t zkgpu_num_witness_cols(const zkgpu_geometry* g);  /* n_copy + boolean + width*reps + multiplicity */
+ZKGPU_API uint32_t zkgpu_num_witness_cols(const zkgpu_geometry* g);  /* n_copy + boolean + width*reps + plain + multiplicity */
 ZKGPU_API uint32_t zkgpu_num_permuted_cols(const zkgpu_geometry* g); /* witness columns under copy permutation     */
 ZKGPU_API uint32_t zkgpu_num_setup_cols(const zkgpu_geometry* g);    /* sigmas + constants + (width+1) table cols   */
 ZKGPU_API uint32_t zkgpu_num_stage2_cols(const zkgpu_geometry* g);   /* 2 * (ceil(perm/qdeg) + reps + (reps?1:0))   */
@@ -181,6 +190,11 @@ ZKGPU_API int zkgpu_verify(const zkgpu_geometry* g, const zkgpu_proof_config* cf
 /* Synthetic satisfying trace for a geometry (stands in for the reference's Rust synthesis, which cannot run in this
  * image): fills witness (W x n) and setup (S x n) columns deterministically from `seed`.  Host only. */
 ZKGPU_API int zkgpu_synth_trace(const zkgpu_geometry* g, uint64_t seed, uint64_t* h_witness_cols, uint64_t* h_setup_cols);
+/* Same, with the two roles of the seed separated: `setup_seed` fixes what belongs to the circuit TYPE (gate constants; the
+ * setup columns depend on it alone), `witness_seed` the free witness values of one circuit INSTANCE -- many instances of
+ * one type share a setup / verification key, as in the reference (src/tests/complex_tests/mod.rs:316-410). */
+ZKGPU_API int zkgpu_synth_trace_instance(const zkgpu_geometry* g, uint64_t setup_seed, uint64_t witness_seed, uint64_t* h_witness_cols,
+                                         uint64_t* h_setup_cols);
 
 #ifdef __cplusplus
 }

@@ -9,22 +9,28 @@
 #include "gl64.h"
 
 static inline uint32_t og_width(uint32_t kind) {
-    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8, 5};
+    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8, 5, 1, 24, 24, 2, 17, 2};
     return kind < ZKGPU_GATE_KINDS ? W[kind] : 0;
 }
 static inline uint32_t og_relations(uint32_t kind) {
-    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2, 1};
+    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2, 1, 1, 12, 12, 1, 8, 2};
     return kind < ZKGPU_GATE_KINDS ? R[kind] : 0;
 }
-static inline uint32_t og_instances(const zkgpu_gate *g, uint32_t n_copy) {
-    uint32_t w = og_width(g->kind);
+/* gate cells: the copy columns followed by the plain witness columns (include/zkgpu.h: n_witness_plain) */
+static inline uint32_t og_instances(const zkgpu_gate *g, const zkgpu_geometry *geo) {
+    uint32_t w = og_width(g->kind), n_copy = geo->n_copy, n_plain = geo->n_witness_plain;
     if (!w) return 0;
-    if (g->kind == ZKGPU_GATE_CONSTANTS_ALLOCATOR) return g->n_consts;
-    return n_copy / w;
+    switch (g->kind) {
+    case ZKGPU_GATE_CONSTANTS_ALLOCATOR: return g->n_consts;
+    case ZKGPU_GATE_POSEIDON2_FLATTENED: return (n_copy + n_plain) / 130;
+    case ZKGPU_GATE_BOUNDED_BOOLEAN: return n_copy < 10 ? n_copy : 10;
+    case ZKGPU_GATE_ZERO_CHECK_WITNESS: return n_copy / 2 < n_plain ? n_copy / 2 : n_plain;
+    default: return n_copy / w;
+    }
 }
 static inline uint32_t og_total_terms(const zkgpu_geometry *geo) {
     uint32_t t = 0;
-    for (uint32_t i = 0; i < geo->n_gates; i++) t += og_instances(&geo->gates[i], geo->n_copy) * og_relations(geo->gates[i].kind);
+    for (uint32_t i = 0; i < geo->n_gates; i++) t += og_instances(&geo->gates[i], geo) * og_relations(geo->gates[i].kind);
     return t;
 }
 
@@ -50,10 +56,11 @@ static void og_p2_internal(uint64_t *s) {
 }
 static inline uint64_t og_pow7(uint64_t x) { return gl_mul(gl_mul(gl_sqr(gl_sqr(x)), gl_sqr(x)), x); }
 
-/* writes the relation values of gate g at one point into out[], returns how many.  v = copy-column values, k = the
- * gate's constants (constant columns starting at path_len), rc = Poseidon2 round constants. */
-static uint32_t og_eval_gate(const zkgpu_gate *g, uint32_t n_copy, const uint64_t *v, const uint64_t *k, const uint64_t *rc, uint64_t *out) {
-    uint32_t inst = og_instances(g, n_copy), n = 0;
+/* writes the relation values of gate g at one point into out[], returns how many.  v = gate CELL values (copy columns,
+ * then plain witness columns), k = the gate's constants (constant columns starting at path_len), rc = Poseidon2 round constants. */
+static uint32_t og_eval_gate(const zkgpu_gate *g, const zkgpu_geometry *geo, const uint64_t *v, const uint64_t *k, const uint64_t *rc, uint64_t *out) {
+    uint32_t inst = og_instances(g, geo), n = 0;
+    const uint32_t n_copy = geo->n_copy;
     switch (g->kind) {
     case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
         for (uint32_t t = 0; t < inst; t++) out[n++] = gl_sub(v[t], k[t]);
@@ -108,6 +115,39 @@ static uint32_t og_eval_gate(const zkgpu_gate *g, uint32_t n_copy, const uint64_
             const uint64_t *x = v + 5 * t;
             uint64_t rhs = gl_add(x[3], gl_mul(x[4], (uint64_t)1 << 32));
             out[n++] = gl_sub(gl_add(gl_add(x[0], x[1]), x[2]), rhs);
+        }
+        break;
+    case ZKGPU_GATE_BOUNDED_BOOLEAN:
+        for (uint32_t t = 0; t < inst; t++) out[n++] = gl_sub(gl_sqr(v[t]), v[t]);
+        break;
+    case ZKGPU_GATE_MATMUL12_EXTERNAL:
+    case ZKGPU_GATE_MATMUL12_INNER:
+        for (uint32_t t = 0; t < inst; t++) {
+            const uint64_t *x = v + 24 * t;
+            uint64_t s[12];
+            for (int i = 0; i < 12; i++) s[i] = x[i];
+            if (g->kind == ZKGPU_GATE_MATMUL12_EXTERNAL) og_p2_external(s);
+            else og_p2_internal(s);
+            for (int i = 0; i < 12; i++) out[n++] = gl_sub(x[12 + i], s[i]);
+        }
+        break;
+    case ZKGPU_GATE_NONLINEARITY7:
+        for (uint32_t t = 0; t < inst; t++) out[n++] = gl_sub(v[2 * t + 1], og_pow7(gl_add(v[2 * t], k[0])));
+        break;
+    case ZKGPU_GATE_CONDITIONAL_SWAP4: /* a[4], b[4], swap, result_a[4], result_b[4] */
+        for (uint32_t t = 0; t < inst; t++) {
+            const uint64_t *x = v + 17 * t;
+            for (int i = 0; i < 4; i++) {
+                /* swap ? b : a  and  swap ? a : b */
+                out[n++] = gl_sub(gl_add(gl_mul(x[8], x[4 + i]), gl_mul(gl_sub(1, x[8]), x[i])), x[9 + i]);
+                out[n++] = gl_sub(gl_add(gl_mul(x[8], x[i]), gl_mul(gl_sub(1, x[8]), x[4 + i])), x[13 + i]);
+            }
+        }
+        break;
+    case ZKGPU_GATE_ZERO_CHECK_WITNESS:
+        for (uint32_t t = 0; t < inst; t++) {
+            out[n++] = gl_sub(gl_mul(v[2 * t], v[n_copy + t]), gl_sub(1, v[2 * t + 1]));
+            out[n++] = gl_mul(v[2 * t], v[2 * t + 1]);
         }
         break;
     case ZKGPU_GATE_DOT_PRODUCT4:

@@ -36,7 +36,7 @@ void orc_fri_fold(const uint64_t *in_c0, const uint64_t *in_c1, int log_dom, uin
 /* ------------------------------------------------------------------ geometry helpers */
 static uint32_t n_lookup_cols(const zkgpu_geometry *g) { return g->lookup_width * g->lookup_reps; }
 static uint32_t n_perm(const zkgpu_geometry *g) { return g->n_copy + (g->has_boolean_col ? 1 : 0) + n_lookup_cols(g); }
-static uint32_t n_wit(const zkgpu_geometry *g) { return n_perm(g) + (g->lookup_reps ? 1 : 0); }
+static uint32_t n_wit(const zkgpu_geometry *g) { return n_perm(g) + g->n_witness_plain + (g->lookup_reps ? 1 : 0); }
 static uint32_t n_setup(const zkgpu_geometry *g) { return n_perm(g) + g->n_const_cols + (g->lookup_reps ? g->lookup_width + 1 : 0); }
 static uint32_t n_chunks(const zkgpu_geometry *g) { return (n_perm(g) + g->quotient_degree - 1) / g->quotient_degree; }
 static uint32_t n_s2_ext(const zkgpu_geometry *g) { return n_chunks(g) + g->lookup_reps + (g->lookup_reps ? 1 : 0); }
@@ -176,7 +176,14 @@ static gl2 quotient_numerator(const zkgpu_geometry *g, const chal_t *ch, const u
     /* 1. gates */
     for (uint32_t gi = 0; gi < g->n_gates; gi++) {
         const zkgpu_gate *gt = &g->gates[gi];
-        uint32_t nrel = og_eval_gate(gt, g->n_copy, w, consts + gt->path_len, ORC_P2_RC, scratch);
+        const uint64_t *cells = w;
+        uint64_t cellbuf[520];
+        if (g->n_witness_plain && NP != g->n_copy) { /* plain witness columns sit after ALL copy-permuted columns */
+            memcpy(cellbuf, w, g->n_copy * 8);
+            memcpy(cellbuf + g->n_copy, w + NP, g->n_witness_plain * 8);
+            cells = cellbuf;
+        }
+        uint32_t nrel = og_eval_gate(gt, g, cells, consts + gt->path_len, ORC_P2_RC, scratch);
         if (!nrel) continue;
         uint64_t sel = 1;
         for (uint32_t b = 0; b < gt->path_len; b++) sel = gl_mul(sel, ((gt->path_bits >> b) & 1) ? consts[b] : gl_sub(1, consts[b]));

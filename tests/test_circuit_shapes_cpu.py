@@ -1,4 +1,4 @@
-"""Every circuit type of the reference (13 base-layer circuits, scheduler, leaf, node): the geometry read from its
+"""Every circuit type of the reference (13 base-layer circuits, scheduler, leaf, node, compression modes 1-4): the geometry read from its
 verification key (tests/golden/vk_shapes.json <- setup/**/vk_*.json) must give, through the column-count formulas of the
 C ABI (zkgpu_num_*_cols, zkgpu_proof_size_u64) and the folding-schedule rule, exactly the oracle widths, opening counts,
 Merkle path lengths and FRI leaf shapes observed in the reference's own golden proofs of that circuit."""
@@ -13,6 +13,8 @@ from era_zkevm_test_harness_b200 import prover_utils as PU
 
 FIXTURE = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
 CIRCUITS = list(G.circuit_geometries_from_fixture(FIXTURE))
+# compression modes 1-4 (+ the wrapper-facing variants): geometry with plain witness columns from compression_N_vk.json
+CIRCUITS += [(k, g, e) for k, g, _cfg, e in G.compression_geometries_from_fixture(FIXTURE)]
 
 
 @pytest.mark.parametrize("key,geo,entry", CIRCUITS, ids=[c[0] for c in CIRCUITS])
@@ -57,5 +59,12 @@ def test_gate_sets_cover_every_reference_gate_index():
     for key, geo, entry in CIRCUITS:
         kinds = [geo.gates[i].kind for i in range(geo.n_gates)]
         assert G.GATE_CONSTANTS_ALLOCATOR in kinds and G.GATE_FMA in kinds, key
+        if key.startswith("compression"):
+            assert G.GATE_CONDITIONAL_SWAP4 in kinds and G.GATE_FMA_EXT in kinds
+            assert (G.GATE_POSEIDON2_FLATTENED in kinds) == (geo.n_witness_plain > 0)   # 130 cells = copy + plain columns
+            if geo.n_witness_plain:
+                assert geo.n_copy + geo.n_witness_plain == 130
+            else:
+                assert G.GATE_MATMUL12_EXTERNAL in kinds and G.GATE_MATMUL12_INNER in kinds and G.GATE_NONLINEARITY7 in kinds
         if key.startswith("recursion"):
             assert G.GATE_FMA_EXT in kinds and G.GATE_POSEIDON2_FLATTENED in kinds

@@ -38,7 +38,7 @@ def proof_shape(path):
 
 
 def main():
-    out = {"base": {}, "recursion": {}}
+    out = {"base": {}, "recursion": {}, "compression": {}}
     for t in range(1, 14):
         name, vk = inner(json.load(open(f"{REF}/setup/base_layer/vk_{t}.json")))
         proofs = sorted(glob.glob(f"{REF}/test_proofs/base_layer/basic_circuit_proof_{t}_*.json"))
@@ -53,6 +53,16 @@ def main():
         shapes = [proof_shape(f"{REF}/test_proofs/recursion_layer/{p}") for p in proofs if os.path.exists(f"{REF}/test_proofs/recursion_layer/{p}")]
         out["recursion"][key] = {"variant": name, "fixed_parameters": vk["fixed_parameters"], "setup_merkle_tree_cap": vk["setup_merkle_tree_cap"],
                                  "proof_shapes": shapes}
+    # compression layer (aux_layer/compression_modes/mode_N.rs): the one-shot VK/proof pairs at the reference root
+    # (src/proof_compression/mod.rs:45-86) and the wrapper-facing mode-1 pair under setup/ and test_proofs/
+    comp = {"1": ("compression_1_vk.json", "compression_1_proof.json", 1), "2": ("compression_2_vk.json", "compression_2_proof.json", 2),
+            "3": ("compression_3_vk.json", "compression_3_proof.json", 3), "4": ("compression_4_vk.json", "compression_4_proof.json", 4),
+            "2_for_wrapper": ("compression_2_for_wrapper_vk.json", "compression_2_for_wrapper_proof.json", 2),
+            "1_for_wrapper": ("setup/aux_layer/compression_for_wrapper_vk_1.json", "test_proofs/aux_layer/compression_for_wrapper_proof_1.json", 1)}
+    for key, (vkf, prf, mode) in comp.items():
+        name, vk = inner(json.load(open(f"{REF}/{vkf}")))
+        out["compression"][key] = {"variant": name or f"CompressionMode{mode}Circuit", "mode": mode, "fixed_parameters": vk["fixed_parameters"],
+                                   "setup_merkle_tree_cap": vk["setup_merkle_tree_cap"], "proof_shapes": [proof_shape(f"{REF}/{prf}")]}
     with open(OUT, "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("wrote", OUT, os.path.getsize(OUT), "bytes")
