@@ -22,6 +22,7 @@ import hashlib
 import os
 import time
 from collections import OrderedDict
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Tuple
 
@@ -160,7 +161,8 @@ def gather_stage(local: Dict[int, np.ndarray], n_jobs: int, device=None, group=N
 
 
 def prove_block(plan: BlockPlan, prove: Callable[[Job, int], np.ndarray], block_seed: int = 0, out_dir: str = None,
-                verify: Callable[[Job, np.ndarray], bool] = None, device=None, group=None, security_level=None):
+                verify: Callable[[Job, np.ndarray], bool] = None, device=None, group=None, security_level=None,
+                prefetch: Callable[[List[Tuple[Job, int]]], None] = None):
     """Runs the plan stage by stage.  Every rank calls this with the same plan.  Returns on rank 0 a dict
     {"proofs": {file: flat proof}, "stages": [{name, jobs, seconds}]}; other ranks get {"proofs": None, ...}.
     Rank 0 holds the gathered proofs of every finished stage and broadcasts the child proofs a stage needs for its seeds."""
@@ -180,7 +182,10 @@ def prove_block(plan: BlockPlan, prove: Callable[[Job, int], np.ndarray], block_
             dist.broadcast(st, src=0, group=group)
             seeds = [int(x) for x in st.cpu().tolist()]
         local = {}
-        for i in assign_jobs(jobs, world, rank):
+        mine = assign_jobs(jobs, world, rank)
+        if prefetch is not None:   # lets the prover start producing this rank's witnesses on host threads
+            prefetch([(jobs[i], seeds[i]) for i in mine])
+        for i in mine:
             local[i] = np.ascontiguousarray(prove(jobs[i], seeds[i]), dtype=np.uint64)
         gathered = gather_stage(local, len(jobs), device=device, group=group)
         if rank == 0:
@@ -202,11 +207,15 @@ class GpuBlockProver:
     come from `setup_source(geometry_key) -> (Geometry, ProofConfig, setup_cols)`; the witness of a job from
     `witness_source(job, geo, seed) -> witness columns` (synthetic traces by default)."""
 
-    def __init__(self, ctx, circuits: Dict[str, Tuple[G.Geometry, G.ProofConfig]], max_resident: int = 6, setup_seed: int = 77):
+    def __init__(self, ctx, circuits: Dict[str, Tuple[G.Geometry, G.ProofConfig]], max_resident: int = 6, setup_seed: int = 77,
+                 host_threads: int = 8):
         self.ctx, self.circuits, self.max_resident, self.setup_seed = ctx, circuits, max_resident, setup_seed
         self.resident: "OrderedDict[str, PU.SetupData]" = OrderedDict()
         self.vk_caps: Dict[str, np.ndarray] = {}
         self.seconds = {"synth_trace": 0.0, "setup": 0.0, "prove": 0.0}
+        self.pool = ThreadPoolExecutor(max_workers=host_threads) if host_threads > 1 else None
+        self.pending = {}   # (geometry key, witness seed) -> future of the witness columns
+        self.pending_setup = {}   # geometry key -> future of the setup columns
 
     def _trace(self, key, witness_seed):
         # setup_seed fixes the circuit TYPE (its setup columns / VK), witness_seed the instance (zkgpu_synth_trace_instance)
@@ -224,7 +233,13 @@ class GpuBlockProver:
             _, old = self.resident.popitem(last=False)
             old.close()
         geo, cfg = self.circuits[key]
-        _, setup_cols = self._trace(key, self.setup_seed)
+        fut = self.pending_setup.pop(key, None)
+        if fut is not None:
+            t0 = time.time()
+            setup_cols = fut.result()
+            self.seconds["synth_trace"] += time.time() - t0
+        else:
+            _, setup_cols = self._trace(key, self.setup_seed)
         t0 = time.time()
         sd = PU.create_setup_data(self.ctx, geo, cfg, setup_cols)
         self.seconds["setup"] += time.time() - t0
@@ -232,15 +247,35 @@ class GpuBlockProver:
         self.vk_caps[key] = sd.vk_cap.copy()
         return sd
 
+    def prefetch(self, jobs_and_seeds):
+        """starts generating the witnesses of the given jobs on host threads (zkgpu_synth_trace_instance releases the GIL)"""
+        if self.pool is None:
+            return
+        for job, seed in jobs_and_seeds:
+            geo = self.circuits[job.geometry_key][0]
+            if job.geometry_key not in self.resident and job.geometry_key not in self.pending_setup:
+                self.pending_setup[job.geometry_key] = self.pool.submit(
+                    lambda g=geo: PU.synth_trace(g, seed=self.setup_seed, witness_seed=self.setup_seed)[1])
+            self.pending[(job.geometry_key, seed)] = self.pool.submit(
+                lambda g=geo, sd=seed: PU.synth_trace(g, seed=self.setup_seed, witness_seed=sd)[0])
+
     def prove(self, job: Job, seed: int) -> np.ndarray:
         sd = self.setup(job.geometry_key)
-        wit, _ = self._trace(job.geometry_key, seed)
+        fut = self.pending.pop((job.geometry_key, seed), None)
+        if fut is not None:
+            t0 = time.time()
+            wit = fut.result()
+            self.seconds["synth_trace"] += time.time() - t0   # only the time the GPU actually waited
+        else:
+            wit, _ = self._trace(job.geometry_key, seed)
         t0 = time.time()
         proof = PU.prove_circuit(self.ctx, sd, wit)
         self.seconds["prove"] += time.time() - t0
         return proof
 
     def close(self):
+        if self.pool is not None:
+            self.pool.shutdown(wait=True, cancel_futures=True)
         for sd in self.resident.values():
             sd.close()
         self.resident.clear()
@@ -248,9 +283,8 @@ class GpuBlockProver:
 
 def circuit_table(fixture, log_n=None, compression_log_n=None):
     """{geometry key: (Geometry, ProofConfig)} for every job kind of a block: the 13 base circuits, 13 leaf circuits
-    (all share the leaf geometry of the fixture), node, scheduler, compression modes 1..4 (their proof configs on the
-    node-layer geometry: the compression circuits themselves are not restated, geometry.compression_layer_proof_config).
-    Also returns the key maps plan_block needs."""
+    (all share the leaf geometry of the fixture), node, scheduler, compression modes 1..4 (geometry and proof config from
+    compression_N_vk.json, geometry.compression_geometries_from_fixture).  Also returns the key maps plan_block needs."""
     table, base_keys, leaf_keys = {}, {}, {}
     rec = {}
     for key, geo, _ in G.circuit_geometries_from_fixture(fixture):
@@ -271,8 +305,11 @@ def circuit_table(fixture, log_n=None, compression_log_n=None):
         k = f"recursion_leaf_{lt}"
         table[k] = rec[leaf_src]
         leaf_keys[lt] = k
-    node_geo = rec[node_key][0]
-    for m, (ln, _lde, _cap) in G.COMPRESSION_MODES.items():
-        ln = ln if compression_log_n is None else compression_log_n
-        table[f"compression_{m}"] = (node_geo.scaled(ln), G.compression_layer_proof_config(m, ln))
+    for key, geo, cfg, _ in G.compression_geometries_from_fixture(fixture):
+        if "for_wrapper" in key:
+            continue
+        if compression_log_n is not None and compression_log_n != geo.log_n:
+            geo = geo.scaled(compression_log_n)
+            cfg = G.make_proof_config(compression_log_n, 1 << cfg.log_lde, cfg.cap_size, security_level=cfg.n_queries * cfg.log_lde)
+        table[key] = (geo, cfg)
     return table, base_keys, leaf_keys, node_key, sched_key
