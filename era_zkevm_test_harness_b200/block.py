@@ -216,6 +216,7 @@ class GpuBlockProver:
         self.pool = ThreadPoolExecutor(max_workers=host_threads) if host_threads > 1 else None
         self.pending = {}   # (geometry key, witness seed) -> future of the witness columns
         self.pending_setup = {}   # geometry key -> future of the setup columns
+        self.prove_ms = {}        # file -> wall ms of the prove call alone (host witness in, proof out)
 
     def _trace(self, key, witness_seed):
         # setup_seed fixes the circuit TYPE (its setup columns / VK), witness_seed the instance (zkgpu_synth_trace_instance)
@@ -270,7 +271,9 @@ class GpuBlockProver:
             wit, _ = self._trace(job.geometry_key, seed)
         t0 = time.time()
         proof = PU.prove_circuit(self.ctx, sd, wit)
-        self.seconds["prove"] += time.time() - t0
+        dt = time.time() - t0
+        self.seconds["prove"] += dt
+        self.prove_ms[job.file] = round(1e3 * dt, 1)
         return proof
 
     def close(self):

@@ -48,8 +48,7 @@ void lde_batch(Ctx* ctx, const uint64_t* d_values, size_t val_stride, uint64_t* 
     ZK_REQUIRE(lde_stride >= (n << log_lde), "lde: lde_stride too small");
     // scratch for the two-pass inverse: first coset region of the LDE output (overwritten afterwards)
     ntt_inverse(ctx, d_values, val_stride, d_mono, mono_stride, d_lde, lde_stride, log_n, n_cols);
-    for (uint32_t c = 0; c < (1u << log_lde); c++)
-        ntt_forward_coset(ctx, d_mono, mono_stride, d_lde + (size_t)c * n, lde_stride, log_n, n_cols, lde_coset_shift(log_n, log_lde, c));
+    ntt_forward_cosets(ctx, d_mono, mono_stride, d_lde, lde_stride, log_n, n_cols, log_lde, 0, 1u << log_lde);
 }
 }  // namespace zk
 

@@ -68,6 +68,8 @@ struct NttPass {
     const uint64_t* twB;
     int LA;
     uint64_t post_scale;     // optional (non-zero, != 1): multiply every output (used for n^-1 when no post twiddle)
+    // batch over blockIdx.z (cosets): element offsets added per z
+    size_t in_z_stride, out_z_stride, pre_e_z_stride, pre_t_z_stride;
 };
 
 __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPass p) {
@@ -78,8 +80,10 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPass p) {
     uint64_t* data = smem + n_sub;          // T * SP
     const int tid = threadIdx.x, nthr = blockDim.x;
     const size_t t0 = (size_t)blockIdx.x * p.T;  // first member (column or row id) of this tile
-    const uint64_t* in = p.in + (size_t)blockIdx.y * p.in_col_stride;
-    uint64_t* out = p.out + (size_t)blockIdx.y * p.out_col_stride;
+    const uint64_t* in = p.in + (size_t)blockIdx.y * p.in_col_stride + (size_t)blockIdx.z * p.in_z_stride;
+    uint64_t* out = p.out + (size_t)blockIdx.y * p.out_col_stride + (size_t)blockIdx.z * p.out_z_stride;
+    const uint64_t* __restrict__ pre_e = p.pre_e ? p.pre_e + (size_t)blockIdx.z * p.pre_e_z_stride : nullptr;
+    const uint64_t* __restrict__ pre_t = p.pre_t ? p.pre_t + (size_t)blockIdx.z * p.pre_t_z_stride : nullptr;
 
     for (int i = tid; i < n_sub - 1; i += nthr) tw_s[i] = p.tw[i];
 
@@ -88,16 +92,16 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(NttPass p) {
         for (int idx = tid; idx < total; idx += nthr) {
             int t = idx % p.T, e = idx / p.T;
             uint64_t v = in[((size_t)e << p.LM) + t0 + t];
-            if (p.pre_e) v = gl::mul(v, p.pre_e[e]);
-            if (p.pre_t) v = gl::mul(v, p.pre_t[t0 + t]);
+            if (pre_e) v = gl::mul(v, pre_e[e]);
+            if (pre_t) v = gl::mul(v, pre_t[t0 + t]);
             data[t * SP + pad_idx(e)] = v;
         }
     } else {
         for (int idx = tid; idx < total; idx += nthr) {
             int e = idx & (n_sub - 1), t = idx >> p.LB;
             uint64_t v = in[((t0 + t) << p.LB) + e];
-            if (p.pre_e) v = gl::mul(v, p.pre_e[e]);
-            if (p.pre_t) v = gl::mul(v, p.pre_t[t0 + t]);
+            if (pre_e) v = gl::mul(v, pre_e[e]);
+            if (pre_t) v = gl::mul(v, pre_t[t0 + t]);
             data[t * SP + pad_idx(e)] = v;
         }
     }
@@ -260,7 +264,7 @@ static int pick_tile(int LB, int LM) {
     return T;
 }
 
-static void launch_pass(Ctx* ctx, NttPass p, int n_polys) {
+static void launch_pass(Ctx* ctx, NttPass p, int n_polys, unsigned n_z = 1) {
     p.T = pick_tile(p.LB, p.LM);
     int n_sub = 1 << p.LB;
     int SP = n_sub + (n_sub >> 5) + 1;
@@ -274,7 +278,7 @@ static void launch_pass(Ctx* ctx, NttPass p, int n_polys) {
         CUDA_CHECK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set[ctx->device & 63] = true;
     }
-    dim3 grid((unsigned)((1u << p.LM) / p.T), (unsigned)n_polys);
+    dim3 grid((unsigned)((1u << p.LM) / p.T), (unsigned)n_polys, n_z);
     ntt_pass_kernel<<<grid, threads, smem, ctx->stream>>>(p);
     CUDA_CHECK(cudaGetLastError());
     ctx->kernel_launches++;
@@ -305,6 +309,76 @@ void ntt_forward_coset(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t*
     q.in = out; q.out = out; q.in_col_stride = out_stride; q.out_col_stride = out_stride;
     q.LB = pl.L2; q.LM = pl.L1; q.in_strided = 0; q.out_strided = 0; q.out_natural = 0; q.tw = pl.tw2;
     launch_pass(ctx, q, n_polys);
+}
+
+// ---- all cosets of an LDE at once
+__global__ void coset_pow_table_kernel(uint64_t* out, const uint64_t* __restrict__ bases, size_t n) {  // out[c][i] = bases[c]^i
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[(size_t)blockIdx.y * n + i] = gl::pow(bases[blockIdx.y], i);
+}
+static const CosetBatchTables& get_coset_batch_tables(Ctx* ctx, int log_n, int log_e) {
+    auto key = std::make_pair(log_n, log_e);
+    auto it = ctx->coset_batch_tables.find(key);
+    if (it != ctx->coset_batch_tables.end()) return it->second;
+    const NttPlan& pl = get_ntt_plan(ctx, log_n, false);
+    const size_t E = (size_t)1 << log_e, ne = (size_t)1 << pl.L1, nt = pl.L2 ? (size_t)1 << pl.L2 : 0;
+    std::vector<uint64_t> h(2 * E);
+    for (size_t c = 0; c < E; c++) {
+        const uint64_t shift = lde_coset_shift(log_n, log_e, (uint32_t)c);
+        h[c] = pl.L2 ? gl::pow(shift, (uint64_t)1 << pl.L2) : shift;   // base of pre_e: shift^(n2*i1), or shift^i for one pass
+        h[E + c] = shift;                                               // base of pre_t
+    }
+    uint64_t* d_bases = (uint64_t*)ctx->alloc_persistent(2 * E * 8);
+    CUDA_CHECK(cudaMemcpyAsync(d_bases, h.data(), 2 * E * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CosetBatchTables t{};
+    t.pre_e = (uint64_t*)ctx->alloc_persistent(E * ne * 8);
+    coset_pow_table_kernel<<<dim3((unsigned)((ne + 127) / 128), (unsigned)E), 128, 0, ctx->stream>>>(t.pre_e, d_bases, ne);
+    CUDA_CHECK(cudaGetLastError());
+    ctx->kernel_launches++;
+    if (nt) {
+        t.pre_t = (uint64_t*)ctx->alloc_persistent(E * nt * 8);
+        coset_pow_table_kernel<<<dim3((unsigned)((nt + 127) / 128), (unsigned)E), 128, 0, ctx->stream>>>(t.pre_t, d_bases + E, nt);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->kernel_launches++;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // h is a stack-lifetime host vector
+    return ctx->coset_batch_tables.emplace(key, t).first->second;
+}
+
+void ntt_forward_cosets(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int log_n, int n_polys, int log_e,
+                        uint32_t c0, uint32_t nc) {
+    if (n_polys == 0 || nc == 0) return;
+    if (log_n == 20) {   // the 2^20 fast path keeps per-coset inter-pass tables (base / recursion layers: 8 cosets)
+        for (uint32_t c = c0; c < c0 + nc; c++)
+            ntt1024_forward_coset(ctx, in, in_stride, out + ((size_t)(c - c0) << 20), out_stride, n_polys, lde_coset_shift(log_n, log_e, c));
+        return;
+    }
+    const NttPlan& pl = get_ntt_plan(ctx, log_n, false);
+    const CosetBatchTables& bt = get_coset_batch_tables(ctx, log_n, log_e);
+    const size_t N = (size_t)1 << log_n, ne = (size_t)1 << pl.L1, nt = pl.L2 ? (size_t)1 << pl.L2 : 0;
+    // grid.z is limited to 65535 and grid.y * grid.z CTAs should stay reasonable: at most 2048 cosets per launch
+    for (uint32_t b0 = 0; b0 < nc; b0 += 2048) {
+        const uint32_t nb = nc - b0 < 2048 ? nc - b0 : 2048;
+        uint64_t* o = out + (size_t)b0 * N;
+        NttPass p{};
+        p.in = in; p.out = o; p.in_col_stride = in_stride; p.out_col_stride = out_stride;
+        p.in_z_stride = 0; p.out_z_stride = N;
+        p.pre_e = bt.pre_e + (size_t)(c0 + b0) * ne; p.pre_e_z_stride = ne;
+        if (pl.L2 == 0) {
+            p.LB = pl.L1; p.LM = 0; p.in_strided = 0; p.out_strided = 0; p.out_natural = 0; p.tw = pl.tw1;
+            launch_pass(ctx, p, n_polys, nb);
+            continue;
+        }
+        p.LB = pl.L1; p.LM = pl.L2; p.in_strided = 1; p.out_strided = 1; p.out_natural = 0; p.tw = pl.tw1;
+        p.pre_t = bt.pre_t + (size_t)(c0 + b0) * nt; p.pre_t_z_stride = nt;
+        p.twA = pl.twA; p.twB = pl.twB; p.LA = pl.LA;
+        launch_pass(ctx, p, n_polys, nb);
+        NttPass q{};
+        q.in = o; q.out = o; q.in_col_stride = out_stride; q.out_col_stride = out_stride;
+        q.in_z_stride = N; q.out_z_stride = N;
+        q.LB = pl.L2; q.LM = pl.L1; q.in_strided = 0; q.out_strided = 0; q.out_natural = 0; q.tw = pl.tw2;
+        launch_pass(ctx, q, n_polys, nb);
+    }
 }
 
 // natural-order evaluations on <w_n> -> natural-order monomials.  `tmp` (same shape as out) is scratch when the

@@ -141,8 +141,7 @@ static void extend_columns(Ctx* ctx, const uint64_t* vals, uint64_t* mono, uint6
     int log_e = (int)ilog2(E);
     // two-pass inverse needs scratch: use the first coset region of the output
     ntt_inverse(ctx, vals, N, mono, N, cosets, (size_t)E * N, log_n, (int)n_cols);
-    for (uint32_t c = 0; c < E; c++)
-        ntt_forward_coset(ctx, mono, N, cosets + (size_t)c * N, (size_t)E * N, log_n, (int)n_cols, lde_coset_shift(log_n, log_e, c));
+    ntt_forward_cosets(ctx, mono, N, cosets, (size_t)E * N, log_n, (int)n_cols, log_e, 0, E);
 }
 
 // ------------------------------------------------------------------------------------------------ stage 2
@@ -619,8 +618,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
     tq.release();
     cos_q.alloc((size_t)Q * LN, stream);
     tree_q.alloc(merkle_tree_digests(LN, cap) * 4, stream);
-    for (uint32_t c = 0; c < L; c++)
-        ntt_forward_coset(ctx, qmono.p, N, cos_q.p + (size_t)c * N, LN, log_n, (int)Q, lde_coset_shift(log_n, (int)cfg.log_lde, c));
+    ntt_forward_cosets(ctx, qmono.p, N, cos_q.p, LN, log_n, (int)Q, (int)cfg.log_lde, 0, L);
     merkle_build(ctx, cos_q.p, LN, Q, LN, 1, cap, tree_q.p);
     d2h(ctx, cap_q.data(), tree_q.p + 4 * merkle_cap_offset(LN, cap), cap * 32);
     tr.absorb(cap_q.data(), cap * 4);

@@ -44,6 +44,12 @@ struct CosetTables {
     uint64_t* pre_e;
     uint64_t* pre_t;
 };
+// powers of EVERY coset shift of a (size, LDE factor) pair: row c holds shift_c^(n2*i1), i1 < 2^L1 (pre_e) and shift_c^i0,
+// i0 < 2^L2 (pre_t), shift_c = lde_coset_shift(log_n, log_e, c).  (2^L1 + 2^L2) * E words: 6 MB for 2^15 x 2048.
+struct CosetBatchTables {
+    uint64_t* pre_e;
+    uint64_t* pre_t;
+};
 
 struct Ctx {
     int device = 0;
@@ -52,6 +58,7 @@ struct Ctx {
     std::vector<void*> persistent;  // freed at destroy
     std::map<int, NttPlan> ntt_plans;
     std::map<std::pair<int, uint64_t>, CosetTables> coset_tables;
+    std::map<std::pair<int, int>, CosetBatchTables> coset_batch_tables;   // key (log_n, log_e)
     uint64_t kernel_launches = 0;
     // per-context scratch arena for one proof at a time (prover.cu): a bump allocator over one cudaMalloc'd block, so a proof
     // performs no driver allocations at all once the arena has reached its size
@@ -70,6 +77,11 @@ struct Ctx {
 const NttPlan& get_ntt_plan(Ctx* ctx, int log_n, bool inverse);
 void ntt_forward_coset(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int log_n, int n_polys,
                        uint64_t shift);
+// the same for cosets c0 .. c0+nc-1 of the 2^log_e-coset LDE in ONE launch per pass: coset c is written at out + (c - c0) * 2^log_n
+// (+ poly * out_stride).  The high-LDE compression proofs (512-2048 cosets of 2^12..2^15 points) are launch- and
+// latency-bound coset by coset; batched, every pass fills the GPU.
+void ntt_forward_cosets(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int log_n, int n_polys, int log_e,
+                        uint32_t c0, uint32_t nc);
 void ntt_inverse(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, uint64_t* tmp, size_t tmp_stride,
                  int log_n, int n_polys);
 void bitrev_copy(Ctx* ctx, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, int log_n, int n_polys);

@@ -87,7 +87,7 @@ def main():
                 "setup_seconds_max_rank": round(float(secs[2]), 2), "wall_seconds": round(wall, 1),
                 "proofs_per_prove_second": round(plan.n_jobs / float(secs[0]), 2),
                 "stages": [{**s, "seconds": round(s["seconds"], 2)} for s in res["stages"]],
-                "rank0_jobs_ms": {f: round(1e3 * t, 1) for f, t in per_job}, "verified": not a.no_verify}
+                "rank0_prove_ms": prover.prove_ms, "rank0_jobs_ms_incl_trace_wait_and_setup": {f: round(1e3 * t, 1) for f, t in per_job}, "verified": not a.no_verify}
         print(json.dumps(line), flush=True)
     prover.close()
     ctx.close()
