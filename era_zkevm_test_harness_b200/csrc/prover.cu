@@ -728,16 +728,28 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         d2h(ctx, fv.data(), fri[NF].p, 2 * DF * 8);
         std::vector<uint64_t> fin0(DF), fin1(DF);
         uint64_t w_inv = gl::inv(gl::omega(ldf)), n_inv = gl::inv((uint64_t)DF % GL_P), s_inv = gl::inv(shift);
-        for (size_t i = 0; i < DF; i++) {  // naive inverse DFT from bit-reversed values, then undo the coset shift
-            uint64_t a0 = 0, a1 = 0;
-            for (size_t pos = 0; pos < DF; pos++) {
-                uint64_t tw = gl::pow(w_inv, (uint64_t)i * gl::bitrev((uint32_t)pos, ldf));
-                a0 = gl::add(a0, gl::mul(fv[pos], tw));
-                a1 = gl::add(a1, gl::mul(fv[DF + pos], tw));
+        // inverse NTT on the host (DF <= final degree x LDE factor: 16 for the base layer, 2048 for compression mode 4):
+        // bit-reversed values -> natural order, radix-2 decimation in time with w^-1, then n^-1 and the coset shift undone
+        {
+            std::vector<uint64_t> tw(DF / 2 ? DF / 2 : 1);
+            uint64_t x = 1;
+            for (size_t j = 0; j < DF / 2; j++) { tw[j] = x; x = gl::mul(x, w_inv); }
+            for (int half = 0; half < 2; half++) {
+                std::vector<uint64_t>& a = half ? fin1 : fin0;
+                // DIT consumes its input in bit-reversed order: the stored order is already that
+                for (size_t pos = 0; pos < DF; pos++) a[pos] = fv[(size_t)half * DF + pos];
+                for (size_t len = 2; len <= DF; len <<= 1) {
+                    const size_t step = DF / len;
+                    for (size_t blk = 0; blk < DF; blk += len)
+                        for (size_t j = 0; j < len / 2; j++) {
+                            uint64_t u = a[blk + j], v = gl::mul(a[blk + j + len / 2], tw[j * step]);
+                            a[blk + j] = gl::add(u, v);
+                            a[blk + j + len / 2] = gl::sub(u, v);
+                        }
+                }
+                uint64_t sc = n_inv;
+                for (size_t i = 0; i < DF; i++) { a[i] = gl::mul(a[i], sc); sc = gl::mul(sc, s_inv); }
             }
-            uint64_t sc = gl::mul(n_inv, gl::pow(s_inv, i));
-            fin0[i] = gl::mul(a0, sc);
-            fin1[i] = gl::mul(a1, sc);
         }
         for (size_t i = sh.n_final; i < DF; i++)
             ZK_REQUIRE(fin0[i] == 0 && fin1[i] == 0, "prove: final FRI polynomial exceeds its degree bound -- the trace does not satisfy the circuit");
