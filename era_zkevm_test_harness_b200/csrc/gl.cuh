@@ -13,6 +13,11 @@
 #define GL_GEN 7ULL
 
 #ifdef __CUDACC__
+// 2^32 - 1 as a value ptxas cannot see through: with the literal, `mad.lo.cc x, 0xffffffff, y` is strength-reduced to a subtract
+// and its `madc.hi` partner is left alone as IMAD.HI.U32 -- quarter rate on sm_100a (tools/microbench/pipes.cu: 29 vs 61
+// thread-ops/clk/SM); with a register operand the pair fuses into ONE IMAD.WIDE.U32 with carry-out.
+static __constant__ uint32_t gl_eps_opaque_c = 0xFFFFFFFFu;
+#define GL_EPS_OPAQUE gl_eps_opaque_c
 #define GL_HD __host__ __device__ __forceinline__
 #else
 #define GL_HD inline
@@ -86,8 +91,9 @@ GL_HD uint64_t mul(uint64_t a, uint64_t b) {
     uint32_t r0, r1;
     asm("{\n\t"
         ".reg .u32 l0,l1,h0,h1,k,c;\n\t"
-        "mul.lo.u32 l0, %2, %4;\n\t"
-        "mul.hi.u32 l1, %2, %4;\n\t"
+        ".reg .u64 w;\n\t"
+        "mul.wide.u32 w, %2, %4;\n\t"
+        "mov.b64 {l0,l1}, w;\n\t"
         "mad.lo.cc.u32 l1, %2, %5, l1;\n\t"
         "madc.hi.u32 h0, %2, %5, 0;\n\t"
         "mad.lo.cc.u32 l1, %3, %4, l1;\n\t"
@@ -100,14 +106,14 @@ GL_HD uint64_t mul(uint64_t a, uint64_t b) {
         "subc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 l0, l0, k;\n\t"
         "subc.u32 l1, l1, 0;\n\t"
-        "mad.lo.cc.u32 l0, h0, 0xffffffff, l0;\n\t"
-        "madc.hi.cc.u32 l1, h0, 0xffffffff, l1;\n\t"
+        "mad.lo.cc.u32 l0, h0, %6, l0;\n\t"
+        "madc.hi.cc.u32 l1, h0, %6, l1;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, l0;\n\t"
-        "madc.hi.u32 %1, c, 0xffffffff, l1;\n\t"
+        "mad.lo.cc.u32 %0, c, %6, l0;\n\t"
+        "madc.hi.u32 %1, c, %6, l1;\n\t"
         "}"
         : "=r"(r0), "=r"(r1)
-        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_EPS_OPAQUE));
     return canon(((uint64_t)r1 << 32) | r0);
 #else
     unsigned __int128 x = (unsigned __int128)a * b;
@@ -174,14 +180,14 @@ __device__ __forceinline__ uint64_t reduce160(uint32_t s0, uint32_t s1, uint32_t
         "subc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 %2, %2, k;\n\t"
         "subc.u32 %3, %3, 0;\n\t"
-        "mad.lo.cc.u32 %2, %4, 0xffffffff, %2;\n\t"
-        "madc.hi.cc.u32 %3, %4, 0xffffffff, %3;\n\t"
+        "mad.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.cc.u32 %3, %4, %6, %3;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, %2;\n\t"
-        "madc.hi.u32 %1, c, 0xffffffff, %3;\n\t"
+        "mad.lo.cc.u32 %0, c, %6, %2;\n\t"
+        "madc.hi.u32 %1, c, %6, %3;\n\t"
         "}"
         : "=r"(r0), "=r"(r1), "+r"(s0), "+r"(s1)
-        : "r"(s2), "r"(s3));
+        : "r"(s2), "r"(s3), "r"(GL_EPS_OPAQUE));
     return sub(canon(((uint64_t)r1 << 32) | r0), (uint64_t)s4 << 32);
 }
 #endif

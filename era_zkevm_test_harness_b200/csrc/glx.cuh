@@ -26,8 +26,9 @@ GL_HD uint64_t mul(uint64_t a, uint64_t b) {
     uint32_t r0, r1;
     asm("{\n\t"
         ".reg .u32 l0,l1,h0,h1,k,c;\n\t"
-        "mul.lo.u32 l0, %2, %4;\n\t"
-        "mul.hi.u32 l1, %2, %4;\n\t"
+        ".reg .u64 w;\n\t"
+        "mul.wide.u32 w, %2, %4;\n\t"
+        "mov.b64 {l0,l1}, w;\n\t"
         "mad.lo.cc.u32 l1, %2, %5, l1;\n\t"
         "madc.hi.u32 h0, %2, %5, 0;\n\t"
         "mad.lo.cc.u32 l1, %3, %4, l1;\n\t"
@@ -40,14 +41,14 @@ GL_HD uint64_t mul(uint64_t a, uint64_t b) {
         "subc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 l0, l0, k;\n\t"
         "subc.u32 l1, l1, 0;\n\t"
-        "mad.lo.cc.u32 l0, h0, 0xffffffff, l0;\n\t"
-        "madc.hi.cc.u32 l1, h0, 0xffffffff, l1;\n\t"
+        "mad.lo.cc.u32 l0, h0, %6, l0;\n\t"
+        "madc.hi.cc.u32 l1, h0, %6, l1;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, l0;\n\t"
-        "madc.hi.u32 %1, c, 0xffffffff, l1;\n\t"
+        "mad.lo.cc.u32 %0, c, %6, l0;\n\t"
+        "madc.hi.u32 %1, c, %6, l1;\n\t"
         "}"
         : "=r"(r0), "=r"(r1)
-        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_EPS_OPAQUE));
     return ((uint64_t)r1 << 32) | r0;
 #else
     unsigned __int128 x = (unsigned __int128)a * b;
@@ -69,14 +70,14 @@ GL_HD uint64_t reduce96(uint64_t lo, uint32_t hi) {
     uint32_t l0 = (uint32_t)lo, l1 = (uint32_t)(lo >> 32), r0, r1;
     asm("{\n\t"
         ".reg .u32 t0,t1,c;\n\t"
-        "mad.lo.cc.u32 t0, %4, 0xffffffff, %2;\n\t"
-        "madc.hi.cc.u32 t1, %4, 0xffffffff, %3;\n\t"
+        "mad.lo.cc.u32 t0, %4, %5, %2;\n\t"
+        "madc.hi.cc.u32 t1, %4, %5, %3;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, t0;\n\t"
-        "madc.hi.u32 %1, c, 0xffffffff, t1;\n\t"
+        "mad.lo.cc.u32 %0, c, %5, t0;\n\t"
+        "madc.hi.u32 %1, c, %5, t1;\n\t"
         "}"
         : "=r"(r0), "=r"(r1)
-        : "r"(l0), "r"(l1), "r"(hi));
+        : "r"(l0), "r"(l1), "r"(hi), "r"(GL_EPS_OPAQUE));
     return ((uint64_t)r1 << 32) | r0;
 #else
     uint64_t m = (uint64_t)hi * GL_EPS;
@@ -151,14 +152,14 @@ GL_HD uint64_t reduce128(uint64_t lo, uint64_t hi) {
         "subc.u32 k, 0, 0;\n\t"
         "sub.cc.u32 %2, %2, k;\n\t"
         "subc.u32 %3, %3, 0;\n\t"
-        "mad.lo.cc.u32 %2, %4, 0xffffffff, %2;\n\t"
-        "madc.hi.cc.u32 %3, %4, 0xffffffff, %3;\n\t"
+        "mad.lo.cc.u32 %2, %4, %6, %2;\n\t"
+        "madc.hi.cc.u32 %3, %4, %6, %3;\n\t"
         "addc.u32 c, 0, 0;\n\t"
-        "mad.lo.cc.u32 %0, c, 0xffffffff, %2;\n\t"
-        "madc.hi.u32 %1, c, 0xffffffff, %3;\n\t"
+        "mad.lo.cc.u32 %0, c, %6, %2;\n\t"
+        "madc.hi.u32 %1, c, %6, %3;\n\t"
         "}"
         : "=r"(r0), "=r"(r1), "+r"(l0), "+r"(l1)
-        : "r"(h0), "r"(h1));
+        : "r"(h0), "r"(h1), "r"(GL_EPS_OPAQUE));
     return ((uint64_t)r1 << 32) | r0;
 #else
     uint64_t hh = hi >> 32, hl = hi & GL_EPS;
