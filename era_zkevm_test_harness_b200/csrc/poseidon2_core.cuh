@@ -56,6 +56,7 @@ GL_HD void p2x_internal(uint64_t (&s)[12]) {
 // dominated at 96 KB of code, profiles/r01_b_*).
 template <typename RC>
 GL_HD void p2x_full_round(uint64_t (&s)[12], const RC& rc, int r) {
+#ifdef ZK_P2_ROTATE_STATE
 #pragma unroll 1
     for (int it = 0; it < 3; it++) {
         uint64_t n0 = glx::pow7(glx::add_canon(s[0], rc[12 * r + 4 * it]));
@@ -66,6 +67,11 @@ GL_HD void p2x_full_round(uint64_t (&s)[12], const RC& rc, int r) {
         for (int i = 0; i < 8; i++) s[i] = s[i + 4];
         s[8] = n0; s[9] = n1; s[10] = n2; s[11] = n3;
     }
+#else
+    // S-box layer in place, 12 lanes straight-line: 3x the S-box code of the rotating form, but no 16 register moves per 4 lanes
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = glx::pow7(glx::add_canon(s[i], rc[12 * r + i]));
+#endif
     p2x_external(s);
 }
 
