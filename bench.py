@@ -131,13 +131,14 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from era_zkevm_test_harness_b200 import GpuContext, geometry as G, prover_utils as PU
+    from era_zkevm_test_harness_b200 import GpuContext, farm, geometry as G, prover_utils as PU
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
     torch.cuda.set_device(local_rank)
+    host_cores = farm.bind_host_to_gpu(local_rank) if world > 1 else 0   # pinned witness buffers on the GPU's NUMA node
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = GpuContext(local_rank)
@@ -277,6 +278,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (1.3 GB witness, 13 GB setup cosets per proof)", "proof_bytes": n_proof * 8,
                        "proof_verified_by_cpu_verifier": verified},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit.nbytes) * world, "d2h_bytes_per_step": n_proof * 8 * world,
+                    "host_cores_bound_per_rank": host_cores,
                     "steps": e2e_steps},
             "gpu_launches": launches, "ms_each_step": per_step, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": extra,
         }

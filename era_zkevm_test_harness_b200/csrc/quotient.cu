@@ -30,7 +30,7 @@ __device__ __forceinline__ uint64_t selector(const uint64_t* __restrict__ kc, si
 }
 
 // ------------------------------------------------------------------------------------------------ general-purpose gates
-__global__ void __launch_bounds__(128) quotient_gates_kernel(const __grid_constant__ QuotParams p) {
+__global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_constant__ QuotParams p) {
     const size_t N = (size_t)1 << p.g.log_n;
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
