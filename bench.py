@@ -5,8 +5,9 @@
 
 One step = one proof of one MainVM-shaped circuit instance (W=156, S2=58, Q=16, S=167 columns, 2^20 rows, lde 2,
 cap 16, 100 queries) over a synthetic satisfying trace.  `value` is measured with the witness resident in HBM
-(zkgpu_prove_device), `e2e` through the public host-buffer call (zkgpu_prove: pinned host witness -> H2D -> prove ->
-proof D2H).  Multi-GPU: independent circuit instances, one per rank per step (weak scaling, no data-path collective);
+(zkgpu_prove_device), `e2e` through the public host-buffer calls with pinned host witnesses, H2D and proof D2H inside the timed
+region: staged (zkgpu_witness_stage of witness k+1 while zkgpu_prove_staged proves witness k -- the reference proves its circuits
+in a loop) as the headline, and the single call zkgpu_prove beside it.  Multi-GPU: independent circuit instances, one per rank per step (weak scaling, no data-path collective);
 NCCL is used once per step to gather the finished proofs to rank 0, as north_star asks.
 """
 import argparse
@@ -177,12 +178,35 @@ def run_ours(args):
         PU.prove_circuit(ctx, sd, wit, proof_out=proof_np)   # pinned host witness -> H2D -> prove -> proof D2H
         gather_proofs()
 
+    # the reference proves its circuits in a loop, so circuit k+1's witness is known while circuit k is proven: its upload is
+    # started (zkgpu_witness_stage, second staging slot) before proof k runs.  Every step's H2D copy is issued inside the timed
+    # region; the first step of a run uploads its own witness without overlap, the last one stages nothing.
+    pipe = {"k": 0, "staged": False, "left": 0}
+
+    def step_e2e_staged():
+        k = pipe["k"]
+        if not pipe["staged"]:
+            PU.stage_witness(ctx, sd, wit, k % 2)
+        pipe["left"] -= 1
+        if pipe["left"] > 0:
+            PU.stage_witness(ctx, sd, wit, (k + 1) % 2)   # the same pinned buffer stands in for the next circuit's witness
+            pipe["staged"] = True
+        else:
+            pipe["staged"] = False
+        PU.prove_staged(ctx, sd, k % 2, proof_out=proof_np)
+        gather_proofs()
+        pipe["k"] = k + 1
+
     per_step = []
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, begin=None):
+        if begin:
+            begin(warmup)
         for _ in range(warmup):
             fn()
         barrier()
+        if begin:
+            begin(steps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.kernel_launches
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -203,8 +227,9 @@ def run_ours(args):
         sampler.start()
     ms_dev, launches = timed(step_device, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
     e2e_steps = max(1, min(args.steps, 3))
+    ms_e2e_single, _ = timed(step_e2e, e2e_steps, 1)
+    ms_e2e, _ = timed(step_e2e_staged, args.steps, 1, begin=lambda n: pipe.update(staged=False, left=n))
 
     # ---- sanity: the last proof verifies (rank 0; CPU verifier)
     verified = None
@@ -268,7 +293,8 @@ def run_ours(args):
     if rank == 0:
         sec_per_step = ms_dev / 1e3 / args.steps
         value = world / sec_per_step
-        e2e_value = world / (ms_e2e / 1e3 / e2e_steps)
+        e2e_value = world / (ms_e2e / 1e3 / args.steps)
+        e2e_single = world / (ms_e2e_single / 1e3 / e2e_steps)
         line = {
             "metric": "base_layer_proofs_per_sec_trace_2^20", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -279,7 +305,10 @@ def run_ours(args):
                        "proof_verified_by_cpu_verifier": verified},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit.nbytes) * world, "d2h_bytes_per_step": n_proof * 8 * world,
                     "host_cores_bound_per_rank": host_cores,
-                    "steps": e2e_steps},
+                    "steps": args.steps,
+                    "mode": "staged: the upload of witness k+1 (zkgpu_witness_stage) overlaps proof k (zkgpu_prove_staged); every copy inside the timed region",
+                    "single_call_value": e2e_single, "single_call_steps": e2e_steps,
+                    "single_call_mode": "zkgpu_prove: chunked upload overlapped with the NTTs of the same proof"},
             "gpu_launches": launches, "ms_each_step": per_step, "clocks": clocks, "roofline": roof, "cpu_baseline": cb, "kernels": extra,
         }
         print(json.dumps(line))

@@ -95,6 +95,12 @@ void zkgpu_ctx_destroy(zkgpu_ctx* ctx) {
     zk::ntt1024_forget(&ctx->c);
     for (void* p : ctx->c.persistent) cudaFree(p);
     if (ctx->c.arena_base) cudaFree(ctx->c.arena_base);
+    if (ctx->c.copy_stream) { cudaStreamSynchronize(ctx->c.copy_stream); cudaStreamDestroy(ctx->c.copy_stream); }
+    for (int k = 0; k < 2; k++) {
+        if (ctx->c.staged[k]) cudaFree(ctx->c.staged[k]);
+        if (ctx->c.staged_ready[k]) cudaEventDestroy(ctx->c.staged_ready[k]);
+        if (ctx->c.staged_free[k]) cudaEventDestroy(ctx->c.staged_free[k]);
+    }
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }

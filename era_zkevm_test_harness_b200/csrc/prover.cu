@@ -904,6 +904,73 @@ int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_
     return rc;
 }
 
+int zkgpu_witness_stage(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_cols, int slot) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_witness_cols, "witness_stage: NULL argument");
+        ZK_REQUIRE(slot == 0 || slot == 1, "witness_stage: slot must be 0 or 1");
+        zk::Ctx& c = ctx->c;
+        CUDA_CHECK(cudaSetDevice(c.device));
+        const size_t words = (size_t)s->s->sh.W * s->s->sh.N;
+        if (!c.copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++)
+            if (!c.staged_ready[k]) {
+                CUDA_CHECK(cudaEventCreateWithFlags(&c.staged_ready[k], cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventCreateWithFlags(&c.staged_free[k], cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventRecord(c.staged_free[k], c.stream));
+            }
+        if (c.staged_words[slot] < words) {   // both slots grow together to the widest circuit seen; steady state allocates nothing
+            CUDA_CHECK(cudaStreamSynchronize(c.stream));
+            CUDA_CHECK(cudaStreamSynchronize(c.copy_stream));
+            for (int k = 0; k < 2; k++) {
+                if (c.staged_words[k] >= words) continue;
+                ZK_REQUIRE(k == slot || c.staged_words[k] == 0 || cudaEventQuery(c.staged_ready[k]) == cudaSuccess,
+                           "witness_stage: cannot grow a slot that holds a pending witness");
+                uint64_t* fresh = nullptr;
+                CUDA_CHECK(cudaMalloc((void**)&fresh, words * 8));
+                if (c.staged[k]) {   // keep a witness already staged in the other slot
+                    CUDA_CHECK(cudaMemcpy(fresh, c.staged[k], c.staged_words[k] * 8, cudaMemcpyDeviceToDevice));
+                    CUDA_CHECK(cudaFree(c.staged[k]));
+                }
+                c.staged[k] = fresh;
+                c.staged_words[k] = words;
+            }
+        }
+        CUDA_CHECK(cudaStreamWaitEvent(c.copy_stream, c.staged_free[slot], 0));   // the proof that last read this slot is done
+        CUDA_CHECK(cudaMemcpyAsync(c.staged[slot], h_witness_cols, words * 8, cudaMemcpyHostToDevice, c.copy_stream));
+        CUDA_CHECK(cudaEventRecord(c.staged_ready[slot], c.copy_stream));
+        c.staged_valid[slot] = true;
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
+}
+
+int zkgpu_prove_staged(zkgpu_ctx* ctx, const zkgpu_setup* s, int slot, uint64_t* h_proof_out, size_t proof_capacity_u64) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_proof_out, "prove_staged: NULL argument");
+        ZK_REQUIRE(slot == 0 || slot == 1, "prove_staged: slot must be 0 or 1");
+        zk::Ctx& c = ctx->c;
+        ZK_REQUIRE(c.staged_valid[slot] && c.staged_words[slot] >= (size_t)s->s->sh.W * s->s->sh.N, "prove_staged: no witness staged in this slot");
+        c.staged_valid[slot] = false;
+        CUDA_CHECK(cudaSetDevice(c.device));
+        CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.staged_ready[slot], 0));
+        zk::prove(&c, *s->s, c.staged[slot], h_proof_out, proof_capacity_u64);
+        CUDA_CHECK(cudaEventRecord(c.staged_free[slot], c.stream));
+        CUDA_CHECK(cudaStreamSynchronize(c.stream));
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
+}
+
 int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_var_maps) {
     try {
         ZK_REQUIRE(ctx && s && s->s && h_var_maps, "set_variable_maps: NULL argument");

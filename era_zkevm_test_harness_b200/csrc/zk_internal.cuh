@@ -64,6 +64,12 @@ struct Ctx {
     // performs no driver allocations at all once the arena has reached its size
     char* arena_base = nullptr;
     size_t arena_cap = 0, arena_off = 0;
+    // two staging slots for witnesses uploaded ahead of their proof (zkgpu_witness_stage / zkgpu_prove_staged)
+    cudaStream_t copy_stream = nullptr;
+    uint64_t* staged[2] = {nullptr, nullptr};
+    size_t staged_words[2] = {0, 0};
+    bool staged_valid[2] = {false, false};
+    cudaEvent_t staged_ready[2] = {nullptr, nullptr}, staged_free[2] = {nullptr, nullptr};
 
     void* alloc_persistent(size_t bytes) {
         void* p = nullptr;

@@ -96,6 +96,22 @@ def prove_circuit(ctx, setup: SetupData, witness_cols, proof_out=None):
     return proof
 
 
+def stage_witness(ctx, setup: SetupData, witness_cols, slot):
+    """Starts the upload of a (pinned) host witness into staging slot 0/1 and returns immediately; prove_staged(slot) proves it.
+    Keep `witness_cols` alive until then."""
+    w = witness_cols
+    assert isinstance(w, np.ndarray) and w.dtype == np.uint64 and w.flags.c_contiguous
+    assert w.shape == (setup.geo.n_witness, 1 << setup.geo.log_n), w.shape
+    _lib.check(ctx.lib.zkgpu_witness_stage(ctx.h, setup.handle, _p(w), slot))
+
+
+def prove_staged(ctx, setup: SetupData, slot, proof_out=None):
+    n_u64 = proof_size_u64(setup.geo, setup.cfg)
+    proof = np.empty(n_u64, dtype=np.uint64) if proof_out is None else proof_out
+    _lib.check(ctx.lib.zkgpu_prove_staged(ctx.h, setup.handle, slot, _p(proof), n_u64))
+    return proof
+
+
 def set_variable_maps(ctx, setup: SetupData, var_maps):
     """var_maps: uint32 [n_perm, n] -- `DenseVariablesCopyHint` of the circuit type (row -> variable index per copy column,
     0xFFFFFFFF = placeholder).  Uploaded once per setup; see prove_from_variables."""

@@ -169,6 +169,14 @@ ZKGPU_API int zkgpu_prove(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* 
 ZKGPU_API int zkgpu_prove_device(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* d_witness_cols, uint64_t* h_proof_out,
                                  size_t proof_capacity_u64);
 
+/* Witness upload ahead of the proof: `basic_test` proves its circuits in a loop (src/tests/complex_tests/mod.rs:316-410), so the
+ * witness of circuit k+1 is known while circuit k is being proven.  zkgpu_witness_stage starts the host->device copy of a
+ * witness into one of two staging slots on the context's copy stream and returns at once (h_witness_cols should be pinned
+ * and must stay valid until the matching zkgpu_prove_staged returns); zkgpu_prove_staged proves the witness of a slot.
+ * Staging slot k+1 before proving slot k hides the PCIe transfer behind the previous proof. */
+ZKGPU_API int zkgpu_witness_stage(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_witness_cols, int slot);
+ZKGPU_API int zkgpu_prove_staged(zkgpu_ctx* ctx, const zkgpu_setup* s, int slot, uint64_t* h_proof_out, size_t proof_capacity_u64);
+
 /* Witness hand-off as the reference does it: boojum's prove_from_precomputations takes `vars_hint: &DenseVariablesCopyHint`
  * (src/prover_utils.rs:346) -- per copy-permutation column a dense map row -> variable index -- and materialises the trace
  * columns itself from the assembly's variable values.  The maps are per circuit TYPE (part of the setup 7-tuple,

@@ -120,3 +120,28 @@ def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
         cfg = G.base_layer_proof_config(9)
         setup = PU.synth_trace(geo, seed=0x5E7)[1]
         assert (np.array(vk["setup_merkle_tree_cap"], dtype=np.uint64) == oracle.setup_cap(geo, cfg, setup)).all()
+
+
+def test_staged_witness_upload_gives_the_same_proofs(gpu):
+    """zkgpu_witness_stage / zkgpu_prove_staged: two instances of one circuit type, the second uploaded while the first is
+    proven; proofs equal the single-call ones, slots can be reused, an empty slot is an error."""
+    geo = G.mainvm_like_geometry(11)
+    cfg = G.make_proof_config(11, 2, 16, security_level=10)
+    wit_a, setup = PU.synth_trace(geo, seed=21, witness_seed=1, pinned=True)
+    wit_b, _ = PU.synth_trace(geo, seed=21, witness_seed=2, pinned=True)
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    ref_a, ref_b = PU.prove_circuit(gpu, sd, wit_a).copy(), PU.prove_circuit(gpu, sd, wit_b).copy()
+    assert not (ref_a == ref_b).all()
+    with pytest.raises(Exception):
+        PU.prove_staged(gpu, sd, 1)
+    PU.stage_witness(gpu, sd, wit_a, 0)
+    PU.stage_witness(gpu, sd, wit_b, 1)
+    got_a = PU.prove_staged(gpu, sd, 0).copy()
+    PU.stage_witness(gpu, sd, wit_b, 0)          # slot 0 is free again: its proof has been read
+    got_b = PU.prove_staged(gpu, sd, 1).copy()
+    got_b2 = PU.prove_staged(gpu, sd, 0).copy()
+    assert (got_a == ref_a).all() and (got_b == ref_b).all() and (got_b2 == ref_b).all()
+    for p in (got_a, got_b):
+        ok, msg = PU.verify_proof(geo, cfg, sd.vk_cap, p)
+        assert ok, msg
+    sd.close()
