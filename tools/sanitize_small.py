@@ -35,5 +35,24 @@ c2 = G.make_proof_config(9, 2, 16, security_level=8)
 w2, s2 = PU.synth_trace(g2, seed=12)
 sd2 = PU.create_setup_data(ctx, g2, c2, s2)
 assert (PU.prove_circuit(ctx, sd2, w2) == oracle.prove(g2, c2, w2, s2)).all()
+# compression mode 2 (plain witness columns, LDE 512: all cosets in one launch per NTT pass) and mode 4 (cap 256, MatMul gates)
+import json  # noqa: E402
+fx = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "vk_shapes.json")))
+for key, cgeo, ccfg, _ in G.compression_geometries_from_fixture(fx):
+    if key not in ("compression_2", "compression_4"):
+        continue
+    g3 = cgeo.scaled(5)
+    c3 = G.make_proof_config(5, 1 << ccfg.log_lde, ccfg.cap_size, security_level=2 * ccfg.log_lde)
+    w3, s3 = PU.synth_trace(g3, seed=13)
+    sd3 = PU.create_setup_data(ctx, g3, c3, s3)
+    assert (PU.prove_circuit(ctx, sd3, w3) == oracle.prove(g3, c3, w3, s3)).all()
+    sd3.close()
+# staged upload: both slots, reuse
+wa, _ = PU.synth_trace(g2, seed=12, pinned=True)
+PU.stage_witness(ctx, sd2, wa, 0)
+PU.stage_witness(ctx, sd2, wa, 1)
+pa = PU.prove_staged(ctx, sd2, 0).copy()
+PU.stage_witness(ctx, sd2, wa, 0)
+assert (PU.prove_staged(ctx, sd2, 1) == pa).all() and (PU.prove_staged(ctx, sd2, 0) == pa).all()
 torch.cuda.synchronize()
 print("sanitize_small: ok")
