@@ -35,6 +35,8 @@ SYMBOLS = {
     "zkgpu_setup_destroy": (None, [ctypes.c_void_p]),
     "zkgpu_prove": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
     "zkgpu_prove_device": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
+    "zkgpu_host_alloc": (ctypes.c_void_p, [sz]),
+    "zkgpu_host_free": (None, [ctypes.c_void_p]),
     "zkgpu_witness_stage": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, ci]),
     "zkgpu_prove_staged": (ci, [ctypes.c_void_p, ctypes.c_void_p, ci, u64p, sz]),
     "zkgpu_setup_set_variable_maps": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p]),

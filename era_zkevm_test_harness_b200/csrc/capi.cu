@@ -105,6 +105,19 @@ void zkgpu_ctx_destroy(zkgpu_ctx* ctx) {
     delete ctx;
 }
 
+void* zkgpu_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        zk::g_last_error = std::string("host_alloc: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    return p;
+}
+void zkgpu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int zkgpu_ctx_synchronize(zkgpu_ctx* ctx) {
     return zk::guarded([&] { CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream)); });
 }

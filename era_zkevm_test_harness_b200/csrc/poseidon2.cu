@@ -35,7 +35,7 @@ void poseidon2_permute_batch(Ctx* ctx, uint64_t* d_states, size_t n_states) {
 // one thread per leaf; leaf i = for each column c: elems_per_leaf consecutive values at cols[c*stride + i*epl ..].
 // The sponge absorbs 8 elements per permutation (overwrite mode, zero padding of the last chunk); the loop is arranged so
 // the permutation has a single call site (code size, see poseidon2_core.cuh).
-__global__ void __launch_bounds__(128) leaf_hash_kernel(const uint64_t* __restrict__ cols, size_t col_stride, int n_cols, size_t n_leaves,
+__global__ void __launch_bounds__(128, 10) leaf_hash_kernel(const uint64_t* __restrict__ cols, size_t col_stride, int n_cols, size_t n_leaves,
                                                         int log_epl, uint64_t* __restrict__ digests) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_leaves) return;
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const uint64_t* __restri
 }
 
 // one thread per node of the next level (wide levels: every lane busy)
-__global__ void __launch_bounds__(128) node_hash_kernel(const uint64_t* __restrict__ prev, uint64_t* __restrict__ next, size_t n_next) {
+__global__ void __launch_bounds__(128, 10) node_hash_kernel(const uint64_t* __restrict__ prev, uint64_t* __restrict__ next, size_t n_next) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_next) return;
     uint64_t s[12];

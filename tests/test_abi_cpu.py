@@ -41,3 +41,12 @@ def test_no_cpu_fallback():
     from era_zkevm_test_harness_b200 import GpuContext
     with pytest.raises(_lib.ZkGpuError):
         GpuContext(0)
+
+
+def test_host_alloc_needs_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    assert not lib.zkgpu_host_alloc(4096) and b"host_alloc" in lib.zkgpu_last_error()
+    lib.zkgpu_host_free(None)

@@ -90,7 +90,8 @@ def test_ntt_2pow20_fast_path_inverse_inplace_and_lde(gpu, oracle):
     assert (to_numpy_u64(lde) == o_lde).all()
 
 
-@pytest.mark.parametrize("log_n,log_lde,n_cols", [(4, 1, 2), (10, 1, 9), (12, 3, 3), (13, 1, 4)])
+# the last three: compression-layer LDE factors (all cosets of an LDE go through one launch per NTT pass, grid.z = coset)
+@pytest.mark.parametrize("log_n,log_lde,n_cols", [(4, 1, 2), (10, 1, 9), (12, 3, 3), (13, 1, 4), (5, 11, 3), (12, 6, 2), (13, 5, 2)])
 def test_lde_matches_oracle(gpu, oracle, log_n, log_lde, n_cols):
     rng = np.random.default_rng(log_n * 10 + log_lde)
     vals = rand_field(rng, (n_cols, 1 << log_n))

@@ -145,3 +145,20 @@ def test_staged_witness_upload_gives_the_same_proofs(gpu):
         ok, msg = PU.verify_proof(geo, cfg, sd.vk_cap, p)
         assert ok, msg
     sd.close()
+
+
+def test_pinned_host_buffers_from_the_library(gpu):
+    """zkgpu_host_alloc gives page-locked memory the prover can read asynchronously; a proof from it equals one from numpy memory"""
+    import ctypes
+    geo = G.small_test_geometry(8, 16, True)
+    cfg = G.make_proof_config(8, 2, 4, security_level=8)
+    wit, setup = PU.synth_trace(geo, seed=4)
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    ptr = gpu.lib.zkgpu_host_alloc(wit.nbytes)
+    assert ptr
+    pinned = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=wit.shape)
+    pinned[:] = wit
+    assert (PU.prove_circuit(gpu, sd, pinned) == PU.prove_circuit(gpu, sd, wit)).all()
+    del pinned
+    gpu.lib.zkgpu_host_free(ptr)
+    sd.close()
