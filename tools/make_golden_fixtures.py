@@ -21,6 +21,13 @@ PROOFS = {
     "mainvm_1_0": "test_proofs/base_layer/basic_circuit_proof_1_0.json",
     "ram_8_0": "test_proofs/base_layer/basic_circuit_proof_8_0.json",
     "node_3_0_0": "test_proofs/recursion_layer/node_layer_proof_3_0_0.json",
+    # compression layer: LDE 32 (2^16), LDE 512 (2^13), and the wrapper-facing variants (LDE 512; LDE 2 at 2^16), final
+    # polynomial of ONE monomial for the first three.  Modes 3 and 4 (last oracle folds by 8 onto a constant) are degenerate for
+    # this hash-free recovery (tools/golden_fri_chain.py).
+    "compression_1": "compression_1_proof.json",
+    "compression_2": "compression_2_proof.json",
+    "compression_2_for_wrapper": "compression_2_for_wrapper_proof.json",
+    "compression_1_for_wrapper": "test_proofs/aux_layer/compression_for_wrapper_proof_1.json",
 }
 N_QUERIES = 16
 
@@ -46,7 +53,7 @@ def main():
             "queries": [
                 {"leaf_indexes": [res["leaf_indexes"][k][q] for k in range(len(res["schedule"]))],
                  "fri_leaves": [fq["leaf_elements"] for fq in Q[q]["fri_queries"]]}
-                for q in range(N_QUERIES)
+                for q in range(min(N_QUERIES, len(Q)))
             ],
         }
         with open(os.path.join(OUT, f"fri_chain_{name}.json"), "w") as f:
