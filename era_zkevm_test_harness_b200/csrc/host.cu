@@ -100,7 +100,8 @@ Shape make_shape(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
     s.n_at_z = s.W + s.S + s.E2 + s.QD;
     s.n_at_zw = 1;
     s.n_at_0 = g.lookup_reps ? g.lookup_reps + 1 : 0;
-    s.n_terms = total_gate_terms(g) + (g.has_boolean_col ? 1 : 0) + g.n_public_inputs + (g.lookup_reps ? g.lookup_reps + 1 : 0) + 1 + s.C;
+    // public inputs are NOT quotient terms: the reference opens them through the DEEP polynomial (pinned on golden proofs)
+    s.n_terms = total_gate_terms(g) + (g.has_boolean_col ? 1 : 0) + (g.lookup_reps ? g.lookup_reps + 1 : 0) + 1 + s.C;
     s.NF = cfg.n_fri_oracles;
     size_t ld = g.log_n + cfg.log_lde;
     for (uint32_t k = 0; k < cfg.n_fri_oracles; k++) {
@@ -399,7 +400,11 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
     const uint64_t* cap_q = p; p += cap * 4;
     const uint64_t* fin0 = p; p += sh.n_final;
     const uint64_t* fin1 = p; p += sh.n_final;
-    const gl::e2* at_z = reinterpret_cast<const gl::e2*>(p); p += 2 * sh.n_at_z;
+    const gl::e2* at_z_proof = reinterpret_cast<const gl::e2*>(p); p += 2 * sh.n_at_z;   // reference order (opening_positions)
+    const std::vector<uint32_t> open_pos = opening_positions(g, sh);
+    std::vector<gl::e2> at_z_v(sh.n_at_z);   // oracle order: witness, setup, stage 2, quotient
+    for (uint32_t i = 0; i < sh.n_at_z; i++) at_z_v[i] = at_z_proof[open_pos[i]];
+    const gl::e2* at_z = at_z_v.data();
     const gl::e2 at_zw = *reinterpret_cast<const gl::e2*>(p); p += 2;
     const gl::e2* at_0 = reinterpret_cast<const gl::e2*>(p); p += 2 * sh.n_at_0;
     const uint64_t* fri_caps[ZKGPU_MAX_FRI_ORACLES];
@@ -417,7 +422,7 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
     gl::e2 alpha = tr.challenge_ext();
     tr.absorb(cap_q, cap * 4);
     gl::e2 z = tr.challenge_ext();
-    tr.absorb(reinterpret_cast<const uint64_t*>(at_z), 2 * sh.n_at_z);
+    tr.absorb(reinterpret_cast<const uint64_t*>(at_z_proof), 2 * sh.n_at_z);
     tr.absorb(at_zw);
     tr.absorb(reinterpret_cast<const uint64_t*>(at_0), 2 * sh.n_at_0);
     gl::e2 phi = tr.challenge_ext();
@@ -455,12 +460,7 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
             ap = gl::mul(ap, alpha);
         }
         const uint64_t n_field = (uint64_t)sh.N % GL_P;
-        for (uint32_t i = 0; i < g.n_public_inputs; i++) {
-            uint64_t wr = gl::pow(gl::omega(g.log_n), g.pi_row[i]);
-            gl::e2 lag = gl::mul(gl::mul_base(zh, wr), gl::inv(gl::mul_base(gl::sub(z, gl::make2(wr, 0)), n_field)));
-            acc = gl::add(acc, gl::mul(ap, gl::mul(lag, gl::sub(w[g.pi_col[i]], gl::make2(pi[i], 0)))));
-            ap = gl::mul(ap, alpha);
-        }
+        // (public inputs are not quotient terms: they are opened through the DEEP polynomial below)
         if (g.lookup_reps) {
             const uint32_t LW = g.lookup_width;
             gl::e2 gp[16];
@@ -505,9 +505,11 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
     }
 
     // ---- queries
-    std::vector<gl::e2> phip(sh.n_at_z + 1 + sh.n_at_0);
-    phip[0] = gl::make2(1, 0);
-    for (size_t i = 1; i < phip.size(); i++) phip[i] = gl::mul(phip[i - 1], phi);
+    // phi powers by position in values_at_z, then z*omega, the openings at 0, the public inputs; phip[] is indexed in oracle order
+    std::vector<gl::e2> phi_pow(sh.n_at_z + 1 + sh.n_at_0 + g.n_public_inputs), phip(phi_pow.size());
+    phi_pow[0] = gl::make2(1, 0);
+    for (size_t i = 1; i < phi_pow.size(); i++) phi_pow[i] = gl::mul(phi_pow[i - 1], phi);
+    for (size_t i = 0; i < phip.size(); i++) phip[i] = i < sh.n_at_z ? phi_pow[open_pos[i]] : phi_pow[i];
     gl::e2 sum_at_z = gl::make2(0, 0);
     for (uint32_t i = 0; i < sh.n_at_z; i++) sum_at_z = gl::add(sum_at_z, gl::mul(phip[i], at_z[i]));
     const uint64_t omega = gl::omega(g.log_n);
@@ -539,6 +541,10 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
         for (uint32_t i = 0; i < sh.n_at_0; i++) {
             gl::e2 a = gl::make2(leaf_2[2 * (sh.C + i)], leaf_2[2 * (sh.C + i) + 1]);
             h = gl::add(h, gl::mul(phip[k++], gl::mul_base(gl::sub(a, at_0[i]), xinv)));
+        }
+        for (uint32_t i = 0; i < g.n_public_inputs; i++) {   // (w_col(x) - value) / (x - omega^row)
+            const uint64_t den = gl::sub(x, gl::pow(omega, g.pi_row[i]));
+            h = gl::add(h, gl::mul_base(phip[k++], gl::mul(gl::sub(leaf_w[g.pi_col[i]], pi[i]), gl::inv(den))));
         }
         // FRI chain
         size_t di = idx;

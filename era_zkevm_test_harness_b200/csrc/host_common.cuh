@@ -32,6 +32,30 @@ struct Shape {
     size_t proof_len;
 };
 Shape make_shape(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
+
+// Position of every opened polynomial inside the proof's `values_at_z` (and so its power of the DEEP challenge).  The code keeps
+// openings internally in ORACLE order -- index i: witness columns [0,W), setup columns [W,W+S), stage-2 Ext2 polys, quotient
+// Ext2 polys -- and permutes at the boundary.  Reference order (boojum's verifier walks values_at_z as: variables, witness
+// columns, constants, copy-permutation sigmas, grand product z, partial products, lookup multiplicities, lookup A polys, lookup B,
+// lookup table columns, quotient chunks).  The lookup-free part of this order -- witness leaf, CONSTANTS, SIGMAS, stage 2,
+// quotient, with the setup leaf itself stored sigmas-then-constants -- is pinned hash-free on the reference's golden proofs
+// compression_1_proof.json and node_layer_proof_3_0_0.json (tools/golden_deep.py); the placement of the four lookup blocks is
+// recalled, not confirmed.
+inline std::vector<uint32_t> opening_positions(const zkgpu_geometry& g, const Shape& sh) {
+    std::vector<uint32_t> pos(sh.n_at_z);
+    uint32_t p = 0;
+    const uint32_t n_wit_first = sh.W - (g.lookup_reps ? 1 : 0);
+    const uint32_t o_s = sh.W, o_2 = sh.W + sh.S, o_q = sh.W + sh.S + sh.E2;
+    for (uint32_t i = 0; i < n_wit_first; i++) pos[i] = p++;                                   // variables, plain witness columns
+    for (uint32_t i = 0; i < g.n_const_cols; i++) pos[o_s + sh.NP + i] = p++;                  // constants
+    for (uint32_t i = 0; i < sh.NP; i++) pos[o_s + i] = p++;                                   // sigmas
+    for (uint32_t i = 0; i < sh.C; i++) pos[o_2 + i] = p++;                                    // z, partial products
+    if (g.lookup_reps) pos[sh.W - 1] = p++;                                                    // multiplicities
+    for (uint32_t i = sh.C; i < sh.E2; i++) pos[o_2 + i] = p++;                                // lookup A polys, B
+    for (uint32_t i = sh.NP + g.n_const_cols; i < sh.S; i++) pos[o_s + i] = p++;               // lookup table columns
+    for (uint32_t i = 0; i < sh.QD; i++) pos[o_q + i] = p++;                                   // quotient chunks
+    return pos;
+}
 void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
 
 constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;

@@ -343,6 +343,8 @@ struct DeepParams {
     const uint64_t* at_0;   // interleaved
     gl::e2 sum_at_z, at_zw, z, zw;
     uint64_t omega_ln;
+    uint32_t n_pi, pi_col[ZKGPU_MAX_PUBLIC_INPUTS];        // public inputs: (w_col(x) - value) / (x - omega^row)
+    uint64_t pi_val[ZKGPU_MAX_PUBLIC_INPUTS], pi_root[ZKGPU_MAX_PUBLIC_INPUTS];
     uint64_t *f0, *f1;
 };
 __global__ void __launch_bounds__(128) deep_kernel(const __grid_constant__ DeepParams p) {
@@ -387,6 +389,14 @@ __global__ void __launch_bounds__(128) deep_kernel(const __grid_constant__ DeepP
         gl::e2 v = gl::make2(p.s2[(size_t)(2 * (p.C + i)) * p.cs_2 + idx], p.s2[(size_t)(2 * (p.C + i) + 1) * p.cs_2 + idx]);
         gl::e2 a0 = gl::make2(p.at_0[2 * i], p.at_0[2 * i + 1]);
         h = gl::add(h, gl::mul(gl::make2(a.x, a.y), gl::mul_base(gl::sub(v, a0), xinv)));
+    }
+    // public inputs (reference: opened through the DEEP polynomial, not constrained in the quotient).  The reference circuits put
+    // all of theirs in ONE row, so consecutive equal roots share the inversion.
+    uint64_t last_root = ~0ULL, last_inv = 0;
+    for (uint32_t i = 0; i < p.n_pi; i++) {
+        ulonglong2 a = phip[k++];
+        if (p.pi_root[i] != last_root) { last_root = p.pi_root[i]; last_inv = gl::inv(gl::sub(x, last_root)); }
+        h = gl::add(h, gl::mul_base(gl::make2(a.x, a.y), gl::mul(gl::sub(p.wit[(size_t)p.pi_col[i] * p.cs_w + idx], p.pi_val[i]), last_inv)));
     }
     p.f0[idx] = h.c0;
     p.f1[idx] = h.c1;
@@ -581,7 +591,6 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.NP = sh.NP; p.C = sh.C; p.E2 = sh.E2; p.W = W; p.lookup_col0 = sh.lookup_col0;
         p.n_field = (uint64_t)N % GL_P;
         p.beta = beta; p.gamma = gamma; p.lbeta = lbeta; p.lgamma = lgamma;
-        for (uint32_t i = 0; i < g.n_public_inputs; i++) { p.pi_values[i] = pi[i]; p.pi_omega[i] = gl::pow(gl::omega(log_n), g.pi_row[i]); }
         {
             uint32_t k = 0;
             p.p2_gate = 0xFFFFFFFFu;
@@ -659,7 +668,11 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         }
         CUDA_CHECK(cudaStreamSynchronize(stream));
     }
-    tr.absorb(reinterpret_cast<const uint64_t*>(at_z.data()), 2 * sh.n_at_z);
+    // at_z is kept in oracle order (witness, setup, stage 2, quotient); the proof and the transcript carry the reference's order
+    const std::vector<uint32_t> open_pos = opening_positions(g, sh);
+    std::vector<gl::e2> at_z_out(sh.n_at_z);
+    for (uint32_t i = 0; i < sh.n_at_z; i++) at_z_out[open_pos[i]] = at_z[i];
+    tr.absorb(reinterpret_cast<const uint64_t*>(at_z_out.data()), 2 * sh.n_at_z);
     tr.absorb(at_zw);
     tr.absorb(reinterpret_cast<const uint64_t*>(at_0.data()), 2 * sh.n_at_0);
     gl::e2 phi = tr.challenge_ext();
@@ -670,13 +683,17 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
     std::vector<DevBuf> fri_tree(NF);
     fri[0].alloc(2 * LN, stream);
     {
-        const uint32_t n_deep = sh.n_at_z + 1 + sh.n_at_0;
+        // weights in the kernel's (oracle) order: phi^(position in values_at_z), then z*omega, the openings at 0, the public inputs
+        const uint32_t n_deep = sh.n_at_z + 1 + sh.n_at_0 + g.n_public_inputs;
+        std::vector<gl::e2> phi_pow(n_deep);
+        phi_pow[0] = gl::make2(1, 0);
+        for (uint32_t i = 1; i < n_deep; i++) phi_pow[i] = gl::mul(phi_pow[i - 1], phi);
         std::vector<uint64_t> phip(2 * (size_t)n_deep);
-        gl::e2 a = gl::make2(1, 0), sum_at_z = gl::make2(0, 0);
+        gl::e2 sum_at_z = gl::make2(0, 0);
         for (uint32_t i = 0; i < n_deep; i++) {
+            const gl::e2 a = i < sh.n_at_z ? phi_pow[open_pos[i]] : phi_pow[i];
             phip[2 * i] = a.c0; phip[2 * i + 1] = a.c1;
             if (i < sh.n_at_z) sum_at_z = gl::add(sum_at_z, gl::mul(a, at_z[i]));
-            a = gl::mul(a, phi);
         }
         DevBuf d_phip, d_at0;
         d_phip.alloc(phip.size(), stream);
@@ -689,6 +706,10 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.W = W; p.S = S; p.E2 = sh.E2; p.QD = QD; p.C = sh.C; p.n_at_0 = sh.n_at_0; p.log_ln = g.log_n + cfg.log_lde;
         p.phip = d_phip.p; p.at_0 = d_at0.p; p.sum_at_z = sum_at_z; p.at_zw = at_zw; p.z = z; p.zw = gl::mul_base(z, gl::omega(log_n));
         p.omega_ln = gl::omega((int)p.log_ln);
+        p.n_pi = g.n_public_inputs;
+        for (uint32_t i = 0; i < g.n_public_inputs; i++) {
+            p.pi_col[i] = g.pi_col[i]; p.pi_val[i] = pi[i]; p.pi_root[i] = gl::pow(gl::omega(log_n), g.pi_row[i]);
+        }
         p.f0 = fri[0].p; p.f1 = fri[0].p + LN;
         deep_kernel<<<(unsigned)((LN + 127) / 128), 128, 0, stream>>>(p);
         LAUNCH_CHECK(ctx);
@@ -767,7 +788,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         memcpy(p, cap_q.data(), cap * 32); p += cap * 4;
         memcpy(p, fin0.data(), sh.n_final * 8); p += sh.n_final;
         memcpy(p, fin1.data(), sh.n_final * 8); p += sh.n_final;
-        memcpy(p, at_z.data(), (size_t)sh.n_at_z * 16); p += 2 * sh.n_at_z;
+        memcpy(p, at_z_out.data(), (size_t)sh.n_at_z * 16); p += 2 * sh.n_at_z;
         memcpy(p, &at_zw, 16); p += 2;
         memcpy(p, at_0.data(), (size_t)sh.n_at_0 * 16); p += 2 * sh.n_at_0;
         for (uint32_t k = 0; k < NF; k++) { memcpy(p, fri_caps[k].data(), sh.fri_cap[k] * 32); p += sh.fri_cap[k] * 4; }

@@ -327,35 +327,9 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
         ulonglong2 a = apow[k++];
         acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::sub(gl::sqr(b), b)));
     }
-    // 3 + 5a. Lagrange denominators N(x - w^row_i) for the public inputs and N(x - 1): one shared inversion
-    uint64_t l0_inv;
-    {
-        uint64_t den[ZKGPU_MAX_PUBLIC_INPUTS + 1], pre[ZKGPU_MAX_PUBLIC_INPUTS + 1];
-        const uint32_t nd = g.n_public_inputs + 1;
-        uint64_t run = 1;
-#pragma unroll 1
-        for (uint32_t i = 0; i < nd; i++) {
-            uint64_t root = i < g.n_public_inputs ? p.pi_omega[i] : 1;
-            den[i] = gl::mul(p.n_field, gl::sub(x, root));
-            pre[i] = run;
-            run = gl::mul(run, den[i]);
-        }
-        uint64_t inv = gl::inv(run);
-        l0_inv = 0;
-#pragma unroll 1
-        for (int i = (int)nd - 1; i >= 0; i--) {
-            uint64_t di = gl::mul(inv, pre[i]);
-            inv = gl::mul(inv, den[i]);
-            if (i == (int)g.n_public_inputs) l0_inv = di;
-            else den[i] = di;
-        }
-#pragma unroll 1
-        for (uint32_t i = 0; i < g.n_public_inputs; i++) {
-            uint64_t lag = gl::mul(gl::mul(p.pi_omega[i], p.xn_minus_1), den[i]);
-            ulonglong2 a = apow[k++];
-            acc = gl::add(acc, gl::mul_base(gl::make2(a.x, a.y), gl::mul(lag, gl::sub(w[(size_t)g.pi_col[i] * cw], p.pi_values[i]))));
-        }
-    }
+    // 5a. Lagrange denominator N(x - 1) of L_0 (public inputs are not quotient terms: the reference opens them through the DEEP
+    // polynomial, prover.cu deep_kernel)
+    const uint64_t l0_inv = gl::inv(gl::mul(p.n_field, gl::sub(x, 1)));
     // 4. lookup
     if (g.lookup_reps) {
         const uint32_t LW = g.lookup_width;

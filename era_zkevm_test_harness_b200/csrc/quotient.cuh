@@ -22,7 +22,6 @@ struct QuotParams {
     uint64_t shift, xn_minus_1, zh_inv, n_field;
     gl::e2 beta, gamma, lbeta, lgamma;
     gl::e2 lgamma_pow[9];                  // lgamma^q, q <= lookup_width
-    uint64_t pi_values[ZKGPU_MAX_PUBLIC_INPUTS], pi_omega[ZKGPU_MAX_PUBLIC_INPUTS];
 };
 
 // one coset of the quotient domain: gates -> (Poseidon2 gate) -> boolean/PI/lookup/copy-permutation and division by Z_H

@@ -46,6 +46,76 @@ EXPORT uint32_t orc_num_witness_cols(const zkgpu_geometry *g) { return n_wit(g);
 EXPORT uint32_t orc_num_setup_cols(const zkgpu_geometry *g) { return n_setup(g); }
 EXPORT uint32_t orc_num_stage2_cols(const zkgpu_geometry *g) { return 2 * n_s2_ext(g); }
 
+/* ------------------------------------------------------------------ DEEP combination at one LDE point
+ * h(x) = sum_i phi^i (F_i(x) - F_i(z)) / (x - z) + phi^n (Z(x) - Z(z w)) / (x - z w) + sum_j phi^.. (A_j(x) - A_j(0)) / x
+ *        + sum_t phi^.. (w_col_t(x) - pi_t) / (x - w^row_t)
+ * F_i in the order of the reference's values_at_z (see the openings section of orc_prove); wl/sl/l2/lq = the four trace-oracle
+ * leaves at x (stage-2 and quotient Ext2 polys as adjacent (c0, c1) columns).  Pinned hash-free on golden proofs for lookup-free
+ * circuits (tests/golden/deep_*.json). */
+typedef struct { int kind; uint32_t idx; } open_src; /* kind 0: witness column, 1: setup column, 2: stage-2 Ext2 poly, 3: quotient Ext2 poly */
+static uint32_t opening_sources(const zkgpu_geometry *g, open_src *src) {
+    const uint32_t NP = n_perm(g), W = n_wit(g), S = n_setup(g), C = n_chunks(g), E2 = n_s2_ext(g), QD = g->quotient_degree;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < W - (g->lookup_reps ? 1 : 0); i++) src[k++] = (open_src){0, i};
+    for (uint32_t i = 0; i < g->n_const_cols; i++) src[k++] = (open_src){1, NP + i};
+    for (uint32_t i = 0; i < NP; i++) src[k++] = (open_src){1, i};
+    for (uint32_t i = 0; i < C; i++) src[k++] = (open_src){2, i};
+    if (g->lookup_reps) src[k++] = (open_src){0, W - 1};
+    for (uint32_t i = C; i < E2; i++) src[k++] = (open_src){2, i};
+    for (uint32_t i = NP + g->n_const_cols; i < S; i++) src[k++] = (open_src){1, i};
+    for (uint32_t i = 0; i < QD; i++) src[k++] = (open_src){3, i};
+    return k;
+}
+static gl2 deep_point(const zkgpu_geometry *g, const open_src *src, uint32_t n_at_z, uint32_t n_at_0, const uint64_t *wl, const uint64_t *sl,
+                      const uint64_t *l2, const uint64_t *lq, const gl2 *phip, gl2 sum_at_z, gl2 at_zw, const gl2 *at_0,
+                      const uint64_t *pi_values, const uint64_t *pi_root, uint64_t x, gl2 z, gl2 zw) {
+    const uint32_t C = n_chunks(g);
+    gl2 s = gl2_make(0, 0);
+    for (uint32_t i = 0; i < n_at_z; i++) {
+        const uint32_t e = src[i].idx;
+        switch (src[i].kind) {
+        case 0: s = gl2_add(s, gl2_mul_base(phip[i], wl[e])); break;
+        case 1: s = gl2_add(s, gl2_mul_base(phip[i], sl[e])); break;
+        case 2: s = gl2_add(s, gl2_mul(phip[i], gl2_make(l2[2 * e], l2[2 * e + 1]))); break;
+        default: s = gl2_add(s, gl2_mul(phip[i], gl2_make(lq[2 * e], lq[2 * e + 1]))); break;
+        }
+    }
+    uint32_t k = n_at_z;
+    gl2 xe = gl2_make(x, 0);
+    gl2 h = gl2_mul(gl2_sub(s, sum_at_z), gl2_inv(gl2_sub(xe, z)));
+    h = gl2_add(h, gl2_mul(gl2_mul(phip[k++], gl2_sub(gl2_make(l2[0], l2[1]), at_zw)), gl2_inv(gl2_sub(xe, zw))));
+    uint64_t xinv = gl_inv(x);
+    for (uint32_t i = 0; i < n_at_0; i++) {
+        gl2 a = gl2_make(l2[2 * (C + i)], l2[2 * (C + i) + 1]);
+        h = gl2_add(h, gl2_mul(phip[k++], gl2_mul_base(gl2_sub(a, at_0[i]), xinv)));
+    }
+    for (uint32_t i = 0; i < g->n_public_inputs; i++) {
+        uint64_t num = gl_sub(wl[g->pi_col[i]], pi_values[i]);
+        h = gl2_add(h, gl2_mul_base(phip[k++], gl_mul(num, gl_inv(gl_sub(x, pi_root[i])))));
+    }
+    return h;
+}
+/* test entry point: the DEEP value at one point from the four leaves and the proof's openings (at_z in the proof's order) */
+EXPORT void orc_deep_at_point(const zkgpu_geometry *g, const uint64_t *wl, const uint64_t *sl, const uint64_t *l2, const uint64_t *lq,
+                              const uint64_t *at_z, const uint64_t *at_zw, const uint64_t *at_0, const uint64_t *pi_values, uint64_t x,
+                              const uint64_t *z2, const uint64_t *phi2, uint64_t *out2) {
+    const uint32_t n_at_z = n_wit(g) + n_setup(g) + n_s2_ext(g) + g->quotient_degree, n_at_0 = g->lookup_reps ? g->lookup_reps + 1 : 0;
+    open_src *src = (open_src *)malloc(sizeof(open_src) * n_at_z);
+    opening_sources(g, src);
+    const uint32_t n_deep = n_at_z + 1 + n_at_0 + g->n_public_inputs;
+    gl2 *phip = (gl2 *)malloc(sizeof(gl2) * n_deep), phi = gl2_make(phi2[0], phi2[1]), z = gl2_make(z2[0], z2[1]);
+    phip[0] = gl2_make(1, 0);
+    for (uint32_t i = 1; i < n_deep; i++) phip[i] = gl2_mul(phip[i - 1], phi);
+    gl2 sum_at_z = gl2_make(0, 0);
+    for (uint32_t i = 0; i < n_at_z; i++) sum_at_z = gl2_add(sum_at_z, gl2_mul(phip[i], gl2_make(at_z[2 * i], at_z[2 * i + 1])));
+    uint64_t pi_root[ZKGPU_MAX_PUBLIC_INPUTS];
+    for (uint32_t i = 0; i < g->n_public_inputs; i++) pi_root[i] = gl_pow(gl_omega(g->log_n), g->pi_row[i]);
+    gl2 h = deep_point(g, src, n_at_z, n_at_0, wl, sl, l2, lq, phip, sum_at_z, gl2_make(at_zw[0], at_zw[1]), (const gl2 *)at_0, pi_values, pi_root,
+                       x, z, gl2_mul_base(z, gl_omega(g->log_n)));
+    out2[0] = h.c0; out2[1] = h.c1;
+    free(src); free(phip);
+}
+
 /* ------------------------------------------------------------------ transcript (Poseidon2 sponge, rate 8, overwrite) */
 typedef struct {
     uint64_t st[12];
@@ -158,7 +228,7 @@ typedef struct {
 } chal_t;
 
 static uint32_t count_terms(const zkgpu_geometry *g) {
-    uint32_t t = og_total_terms(g) + (g->has_boolean_col ? 1 : 0) + g->n_public_inputs;
+    uint32_t t = og_total_terms(g) + (g->has_boolean_col ? 1 : 0); /* public inputs: DEEP openings, not quotient terms */
     if (g->lookup_reps) t += g->lookup_reps + 1;
     t += 1 + n_chunks(g);
     return t;
@@ -197,12 +267,7 @@ static gl2 quotient_numerator(const zkgpu_geometry *g, const chal_t *ch, const u
         uint64_t b = w[g->n_copy];
         acc = gl2_add(acc, gl2_mul_base(ch->alpha_pow[k++], gl_sub(gl_sqr(b), b)));
     }
-    /* 3. public inputs: L_row(x) * (w_col(x) - value), L_row(x) = omega^row (x^N - 1) / (N (x - omega^row)) */
-    for (uint32_t i = 0; i < g->n_public_inputs; i++) {
-        uint64_t wr = gl_pow(gl_omega(g->log_n), g->pi_row[i]);
-        uint64_t lag = gl_mul(gl_mul(wr, xn_minus_1), gl_inv(gl_mul(N % GL_P, gl_sub(x, wr))));
-        acc = gl2_add(acc, gl2_mul_base(ch->alpha_pow[k++], gl_mul(lag, gl_sub(w[g->pi_col[i]], ch->pi_values[i]))));
-    }
+    /* 3. (public inputs are opened through the DEEP polynomial -- see the DEEP section -- and are not quotient terms) */
     /* 4. lookup (log-derivative): A_i * den_i - 1 ; B * den_table - m */
     if (g->lookup_reps) {
         const uint32_t LW = g->lookup_width;
@@ -403,19 +468,22 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     tr_absorb(&tr, tree_q + cap_off, cap * 4);
     gl2 z = tr_challenge_ext(&tr);
 
-    /* ---- openings */
+    /* ---- openings, in the order of the reference's `values_at_z`: variables + plain witness columns, constants, sigmas,
+     * z + partial products, lookup multiplicities, lookup A polys + B, lookup table columns, quotient chunks.  The lookup-free
+     * part (witness leaf, constants, sigmas, stage 2, quotient; setup leaf stored sigmas-then-constants) is pinned hash-free on
+     * golden proofs (tools/golden_deep.py, tests/golden/deep_*.json); the position of the lookup blocks is recalled. */
     const uint32_t n_at_z = sh.n_at_z, n_at_0 = sh.n_at_0;
+    open_src *src = (open_src *)malloc(sizeof(open_src) * n_at_z);
+    if (opening_sources(g, src) != n_at_z) { fprintf(stderr, "oracle: opening count mismatch\n"); return -1; }
     gl2 *at_z = (gl2 *)malloc(sizeof(gl2) * n_at_z), *at_0 = (gl2 *)malloc(sizeof(gl2) * (n_at_0 ? n_at_0 : 1));
 #pragma omp parallel for schedule(dynamic)
-    for (size_t i = 0; i < (size_t)(W + S + E2 + QD); i++) {
-        if (i < W) at_z[i] = eval_at_ext(mono_w + i * N, N, z);
-        else if (i < W + S) at_z[i] = eval_at_ext(mono_s + (i - W) * N, N, z);
-        else if (i < W + S + E2) {
-            size_t e = i - W - S;
-            at_z[i] = gl2_add(eval_at_ext(mono_2 + (2 * e) * N, N, z), mul_by_u(eval_at_ext(mono_2 + (2 * e + 1) * N, N, z)));
-        } else {
-            size_t e = i - W - S - E2;
-            at_z[i] = gl2_add(eval_at_ext(mono_q + (2 * e) * N, N, z), mul_by_u(eval_at_ext(mono_q + (2 * e + 1) * N, N, z)));
+    for (size_t i = 0; i < (size_t)n_at_z; i++) {
+        const uint32_t e = src[i].idx;
+        switch (src[i].kind) {
+        case 0: at_z[i] = eval_at_ext(mono_w + (size_t)e * N, N, z); break;
+        case 1: at_z[i] = eval_at_ext(mono_s + (size_t)e * N, N, z); break;
+        case 2: at_z[i] = gl2_add(eval_at_ext(mono_2 + (size_t)(2 * e) * N, N, z), mul_by_u(eval_at_ext(mono_2 + (size_t)(2 * e + 1) * N, N, z))); break;
+        default: at_z[i] = gl2_add(eval_at_ext(mono_q + (size_t)(2 * e) * N, N, z), mul_by_u(eval_at_ext(mono_q + (size_t)(2 * e + 1) * N, N, z))); break;
         }
     }
     gl2 zw = gl2_mul_base(z, omega);
@@ -427,7 +495,7 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     gl2 phi = tr_challenge_ext(&tr);
 
     /* ---- DEEP polynomial on the LDE domain */
-    const uint32_t n_deep = n_at_z + 1 + n_at_0;
+    const uint32_t n_deep = n_at_z + 1 + n_at_0 + g->n_public_inputs;
     gl2 *phip = (gl2 *)malloc(sizeof(gl2) * n_deep);
     phip[0] = gl2_make(1, 0);
     for (uint32_t i = 1; i < n_deep; i++) phip[i] = gl2_mul(phip[i - 1], phi);
@@ -436,25 +504,22 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     uint64_t *f0 = alloc_u64(LN), *f1 = alloc_u64(LN);
     const int log_ln = log_n + log_lde;
     const uint64_t omega_ln = gl_omega(log_ln);
-#pragma omp parallel for schedule(static)
-    for (size_t idx = 0; idx < LN; idx++) {
-        uint64_t x = gl_mul(GL_GEN, gl_pow(omega_ln, bitrev32((uint32_t)idx, log_ln)));
-        gl2 s = gl2_make(0, 0);
-        uint32_t k = 0;
-        for (uint32_t i = 0; i < W; i++) s = gl2_add(s, gl2_mul_base(phip[k++], lde_w[(size_t)i * LN + idx]));
-        for (uint32_t i = 0; i < S; i++) s = gl2_add(s, gl2_mul_base(phip[k++], lde_s[(size_t)i * LN + idx]));
-        for (uint32_t i = 0; i < E2; i++) s = gl2_add(s, gl2_mul(phip[k++], gl2_make(lde_2[(size_t)(2 * i) * LN + idx], lde_2[(size_t)(2 * i + 1) * LN + idx])));
-        for (uint32_t i = 0; i < QD; i++) s = gl2_add(s, gl2_mul(phip[k++], gl2_make(lde_q[(size_t)(2 * i) * LN + idx], lde_q[(size_t)(2 * i + 1) * LN + idx])));
-        gl2 xe = gl2_make(x, 0);
-        gl2 h = gl2_mul(gl2_sub(s, sum_at_z), gl2_inv(gl2_sub(xe, z)));
-        gl2 zp = gl2_make(lde_2[idx], lde_2[LN + idx]);
-        h = gl2_add(h, gl2_mul(gl2_mul(phip[k++], gl2_sub(zp, at_zw)), gl2_inv(gl2_sub(xe, zw))));
-        uint64_t xinv = gl_inv(x);
-        for (uint32_t i = 0; i < n_at_0; i++) {
-            gl2 a = gl2_make(lde_2[(size_t)(2 * (C + i)) * LN + idx], lde_2[(size_t)(2 * (C + i) + 1) * LN + idx]);
-            h = gl2_add(h, gl2_mul(phip[k++], gl2_mul_base(gl2_sub(a, at_0[i]), xinv)));
+    uint64_t pi_root[ZKGPU_MAX_PUBLIC_INPUTS];
+    for (uint32_t i = 0; i < g->n_public_inputs; i++) pi_root[i] = gl_pow(omega, g->pi_row[i]);
+#pragma omp parallel
+    {
+        uint64_t *wl = alloc_u64(W), *sl = alloc_u64(S), *l2 = alloc_u64(S2), *lq = alloc_u64(Q);
+#pragma omp for schedule(static)
+        for (size_t idx = 0; idx < LN; idx++) {
+            uint64_t x = gl_mul(GL_GEN, gl_pow(omega_ln, bitrev32((uint32_t)idx, log_ln)));
+            for (uint32_t i = 0; i < W; i++) wl[i] = lde_w[(size_t)i * LN + idx];
+            for (uint32_t i = 0; i < S; i++) sl[i] = lde_s[(size_t)i * LN + idx];
+            for (uint32_t i = 0; i < S2; i++) l2[i] = lde_2[(size_t)i * LN + idx];
+            for (uint32_t i = 0; i < Q; i++) lq[i] = lde_q[(size_t)i * LN + idx];
+            gl2 h = deep_point(g, src, n_at_z, n_at_0, wl, sl, l2, lq, phip, sum_at_z, at_zw, at_0, pi_values, pi_root, x, z, zw);
+            f0[idx] = h.c0; f1[idx] = h.c1;
         }
-        f0[idx] = h.c0; f1[idx] = h.c1;
+        free(wl); free(sl); free(l2); free(lq);
     }
 
     /* ---- FRI */

@@ -48,6 +48,7 @@ class Oracle:
         L.orc_proof_size_u64.restype = sz; L.orc_proof_size_u64.argtypes = [vp, vp]
         L.orc_setup_cap.argtypes = [vp, vp, vp, vp]
         L.orc_prove.restype = ctypes.c_long; L.orc_prove.argtypes = [vp, vp, vp, vp, vp, sz]
+        L.orc_deep_at_point.argtypes = [vp] * 9 + [c_u64, vp, vp, vp]
         for nm in ("orc_num_witness_cols", "orc_num_setup_cols", "orc_num_stage2_cols"):
             getattr(L, nm).restype = ctypes.c_uint32; getattr(L, nm).argtypes = [vp]
         L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
@@ -162,6 +163,14 @@ class Oracle:
         w = self.lib.orc_prove(ctypes.byref(geo), ctypes.byref(cfg), self._p(wit_cols), self._p(setup_cols), self._p(proof), n)
         assert w == n, (w, n)
         return proof
+
+    def deep_at_point(self, geo, wl, sl, l2, lq, at_z, at_zw, at_0, pi, x, z, phi):
+        """DEEP combination at one LDE point (oracle/prover.c deep_point): leaves of the four trace oracles at x, openings in
+        the proof's order"""
+        a = [np.ascontiguousarray(v, dtype=np.uint64).reshape(-1) for v in (wl, sl, l2, lq, at_z, at_zw, at_0 if len(at_0) else [0], pi if len(pi) else [0])]
+        zz, pp, out = np.array(z, dtype=np.uint64), np.array(phi, dtype=np.uint64), np.zeros(2, dtype=np.uint64)
+        self.lib.orc_deep_at_point(ctypes.byref(geo), *[self._p(v) for v in a], c_u64(int(x)), self._p(zz), self._p(pp), self._p(out))
+        return (int(out[0]), int(out[1]))
 
     def vec(self, name, *arrs):
         arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]

@@ -178,3 +178,27 @@ def test_golden_fri_chain(oracle, fixture):
                 ld = logd[-1]
                 x = oracle.pow(7, 1 << (logd[0] - ld)) * pow(oracle.omega(ld), brev(m, ld), P) % P
                 assert got == oracle.eval_ext_poly_at_base(mon[0], mon[1], x)
+
+
+@pytest.mark.parametrize("fixture", sorted(glob.glob(os.path.join(GOLDEN, "deep_*.json"))))
+def test_golden_deep_structure(oracle, fixture):
+    """Reference golden proofs (lookup-free circuits): with phi and z recovered WITHOUT the hash (tools/golden_deep.py), the
+    oracle's DEEP combination of the four trace-oracle leaves of a query -- openings paired in the order of the proof's
+    values_at_z (witness leaf, constants, sigmas, stage 2, quotient), the z*omega opening of the grand product, the public inputs
+    opened at omega^row -- reproduces the value the proof holds in its FRI base oracle, bit for bit."""
+    from era_zkevm_test_harness_b200 import geometry as G
+    fx = json.load(open(fixture))
+    assert fx["all_fixture_queries_consistent"]
+    shapes = json.load(open(os.path.join(GOLDEN, "vk_shapes.json")))
+    entry = shapes[fx["shape_key"][0]][fx["shape_key"][1]]
+    if fx["shape_key"][0] == "compression":
+        mode = entry["mode"]
+        geo = G.geometry_from_vk(entry, G.COMPRESSION_GATE_ORDER[mode], has_boolean_col=1 if mode == 1 else 0)
+    else:
+        geo = G.geometry_from_vk(entry, G.RECURSION_GATE_ORDER)
+    assert geo.lookup_reps == 0 and len(fx["values_at_z"]) == geo.n_witness + geo.n_setup + geo.n_stage2 // 2 + geo.n_quotient // 2
+    for q in fx["queries"]:
+        assert len(q["witness"]) == geo.n_witness and len(q["setup"]) == geo.n_setup
+        got = oracle.deep_at_point(geo, q["witness"], q["setup"], q["stage_2"], q["quotient"], fx["values_at_z"], fx["values_at_z_omega"][0],
+                                   fx["values_at_0"], fx["public_inputs"], q["x"], fx["z"], fx["phi"])
+        assert got == tuple(q["fri_base_value"])

@@ -61,5 +61,64 @@ def main():
         print(name, "ok", fx["all_queries_consistent"])
 
 
+# ---- DEEP structure: phi, z and the query positions recovered hash-free (tools/golden_deep.py) for lookup-free circuits
+DEEP = {   # name -> (proof, VK with the public-input locations, key of the circuit in tests/golden/vk_shapes.json)
+    "node_3_0_0": ("test_proofs/recursion_layer/node_layer_proof_3_0_0.json", "setup/recursion_layer/vk_node.json", ["recursion", "node"]),
+    "compression_1": ("compression_1_proof.json", "compression_1_vk.json", ["compression", "1"]),
+}
+N_DEEP_QUERIES = 6
+
+
+def deep_fixtures():
+    import golden_deep
+    from golden_fri_chain import P, omega, brev
+    for name, (rel, vk_rel, shape_key) in DEEP.items():
+        vk = json.load(open(os.path.join(REF, vk_rel)))
+        if "fixed_parameters" not in vk:
+            vk = vk[list(vk.keys())[0]]
+        fp = vk["fixed_parameters"]
+        pil = fp["public_inputs_locations"]
+        par = fp["parameters"]
+        n_perm = par["num_columns_under_copy_permutation"] + (0 if shape_key == ["compression", "2"] else 1)   # + boolean column
+        n_const = par["num_constant_columns"] + fp["extra_constant_polys_for_selectors"]
+
+        def order(w, s, s2, qq):
+            b = lambda v: (v, 0)
+            sig, con = s[:n_perm], s[n_perm:n_perm + n_const]
+            s2e = [(s2[2 * e], s2[2 * e + 1]) for e in range(len(s2) // 2)]
+            qe = [(qq[2 * e], qq[2 * e + 1]) for e in range(len(qq) // 2)]
+            return [b(v) for v in w] + [b(v) for v in con] + [b(v) for v in sig] + s2e + qe, s2e[0], []
+
+        fx_path = os.path.join(OUT, f"fri_chain_{name}.json")
+        res, _ = golden_deep.solve(os.path.join(REF, rel), fx_path, order=order, pi_locs=pil)
+        assert len(res) == 1 and res[0]["consistent"], name
+        r = res[0]
+        fx = json.load(open(fx_path))
+        pr = json.load(open(os.path.join(REF, rel)))
+        if "proof_config" not in pr:
+            pr = pr[list(pr.keys())[0]]
+        log_dom = fx["log_domains"][0]
+        qs = []
+        for q in range(N_DEEP_QUERIES):
+            Q = pr["queries_per_fri_repetition"][q]
+            pos = r["positions"][q]
+            idx = (fx["queries"][q]["leaf_indexes"][0] << 3) + pos
+            fl = Q["fri_queries"][0]["leaf_elements"]
+            qs.append({"lde_index": idx, "x": 7 * pow(omega(log_dom), brev(idx, log_dom), P) % P,
+                       "witness": Q["witness_query"]["leaf_elements"], "setup": Q["setup_query"]["leaf_elements"],
+                       "stage_2": Q["stage_2_query"]["leaf_elements"], "quotient": Q["quotient_query"]["leaf_elements"],
+                       "fri_base_value": [fl[pos], fl[len(fl) // 2 + pos]]})
+        out = {"source": rel, "shape_key": shape_key, "phi": list(r["phi"]), "z": list(r["z"]),
+               "all_fixture_queries_consistent": r["consistent"], "positions_in_fri_leaf": r["positions"],
+               "public_inputs": pr["public_inputs"], "values_at_z": [c["coeffs"] for c in pr["values_at_z"]],
+               "values_at_z_omega": [c["coeffs"] for c in pr["values_at_z_omega"]], "values_at_0": [c["coeffs"] for c in pr["values_at_0"]],
+               "queries": qs}
+        with open(os.path.join(OUT, f"deep_{name}.json"), "w") as f:
+            json.dump(out, f)
+        print("deep", name, "ok")
+
+
 if __name__ == "__main__":
-    main()
+    if "--deep-only" not in sys.argv:
+        main()
+    deep_fixtures()
