@@ -202,3 +202,16 @@ def test_golden_deep_structure(oracle, fixture):
         got = oracle.deep_at_point(geo, q["witness"], q["setup"], q["stage_2"], q["quotient"], fx["values_at_z"], fx["values_at_z_omega"][0],
                                    fx["values_at_0"], fx["public_inputs"], q["x"], fx["z"], fx["phi"])
         assert got == tuple(q["fri_base_value"])
+
+
+def test_golden_lookup_sum_check_at_zero():
+    """values_at_0 of every golden base-layer proof (fixture: the raw openings): the log-derivative lookup identity
+    sum_i A_i(0) = B(0) holds with the openings in the order [A_0 .. A_{reps-1}, B] -- the order and the check of the verifier
+    (csrc/host.cu "lookup sum check") -- without going through the hash."""
+    fx = json.load(open(os.path.join(GOLDEN, "values_at_0.json")))
+    assert len(fx) >= 18
+    for name, vals in fx.items():
+        assert len(vals) >= 2, name
+        s0 = sum(v[0] for v in vals[:-1]) % P
+        s1 = sum(v[1] for v in vals[:-1]) % P
+        assert [s0, s1] == vals[-1], name
