@@ -5,8 +5,11 @@ DEEP (quotening) structure this framework restates (oracle/prover.c "DEEP polyno
   h(x) = sum_{i < n_z} phi^i (F_i(x) - F_i(z)) / (x - z)  +  phi^{n_z} (Z(x) - Z(z w)) / (x - z w)
          + sum_j phi^{n_z + 1 + j} (A_j(x) - A_j(0)) / x
 
-with F_i in the order of `values_at_z` = [witness leaf][setup leaf][stage-2 Ext2 polys][quotient Ext2 polys], Z = stage-2 poly 0,
-A_j = the lookup polys (stage-2 polys C.. ), h = the base FRI oracle.  Known per query without the hash: the leaf of every trace
+         + sum_t phi^{..} (w_col_t(x) - pi_t) / (x - w^row_t)            (public inputs, `pi_locs`)
+
+with F_i in a caller-chosen order (`order`: the pairing of leaf elements with `values_at_z` is the hypothesis under test; the
+order confirmed on golden proofs is [witness leaf][constants][sigmas][stage-2 Ext2 polys][quotient Ext2 polys]), Z = stage-2
+poly 0, A_j = the lookup polys (stage-2 polys C.. ), h = the base FRI oracle.  Known per query without the hash: the leaf of every trace
 oracle at the query point, the 8 values of the FRI base-oracle leaf and its index (tools/golden_fri_chain.py), all openings.
 Unknown: phi, z (Ext2) and the position j of the query point inside its FRI leaf.  Multiplying out gives
 E_{q,j}(phi, z) = a + b z + c z^2 = 0 with polynomials a, b, c in phi; tools/deep/deep_solve.c eliminates z (resultant of two
@@ -63,7 +66,6 @@ def polys_for(pr, q, m0, j, log_dom, order, pi_locs=None, log_n=None, pi_first=F
             den = (x - pow(om_n, row, P)) % P
             M[base_pi + t] = esc(es((w[col], 0), (pr["public_inputs"][t], 0)), pow(den, P - 2, P))
     M[0] = es(M[0], h)
-    w1 = omega(log_dom - 1)            # omega of the trace domain: the LDE domain is twice (lde 2) ... see caller
     return x, T, U, M, n
 
 
