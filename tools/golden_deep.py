@@ -26,7 +26,7 @@ def ext(c):
     return (c["coeffs"][0], c["coeffs"][1])
 
 
-def polys_for(pr, q, m0, j, log_dom, order, pi_locs=None, log_n=None, pi_first=False):
+def polys_for(pr, q, m0, j, log_dom, order, pi_locs=None, log_n=None, pi_first=False, tail=None):
     Q = pr["queries_per_fri_repetition"][q]
     idx = (m0 << 3) + j
     x = 7 * pow(omega(log_dom), brev(idx, log_dom), P) % P
@@ -52,12 +52,17 @@ def polys_for(pr, q, m0, j, log_dom, order, pi_locs=None, log_n=None, pi_first=F
         lookups = s2e[C:]
     n = n_z + 1 + len(at0) + (len(pi_locs) if pi_locs else 0)
     T = [es(F[i], V[i]) for i in range(n_z)] + [ZERO] * (n - n_z)
-    U = [ZERO] * n; U[n_z] = es(zpoly, zw_val)
+    n_pi = len(pi_locs) if pi_locs else 0
+    # order of the three groups after the openings at z: "w" = z*omega (1 term), "0" = openings at 0, "p" = public inputs
+    tail = tail or ("w0p" if not pi_first else "wp0")
+    off, pos_of = n_z, {}
+    for ch in tail:
+        pos_of[ch] = off
+        off += {"w": 1, "0": len(at0), "p": n_pi}[ch]
+    U = [ZERO] * n; U[pos_of["w"]] = es(zpoly, zw_val)
     xinv = pow(x, P - 2, P)
     M = [ZERO] * n
-    n_pi = len(pi_locs) if pi_locs else 0
-    base0 = n_z + 1 + (n_pi if pi_first else 0)        # first phi power of the openings at 0
-    base_pi = n_z + 1 + (0 if pi_first else len(at0))  # first phi power of the public-input openings
+    base0, base_pi = pos_of["0"], pos_of["p"]
     for t in range(len(at0)):
         M[base0 + t] = esc(es(lookups[t], at0[t]), xinv)
     if pi_locs:   # public inputs as openings of variable columns at w^row: (w_col(x) - value) / (x - w^row)
@@ -69,14 +74,14 @@ def polys_for(pr, q, m0, j, log_dom, order, pi_locs=None, log_n=None, pi_first=F
     return x, T, U, M, n
 
 
-def build(pr, fx, qs, order, log_n, pi_locs=None, pi_first=False):
+def build(pr, fx, qs, order, log_n, pi_locs=None, pi_first=False, tail=None):
     log_dom = fx["log_domains"][0]
     om = omega(log_n)
     out = {}
     for q in qs:
         m0 = fx["queries"][q]["leaf_indexes"][0]
         for j in range(8):
-            x, T, U, M, n = polys_for(pr, q, m0, j, log_dom, order, pi_locs, log_n, pi_first)
+            x, T, U, M, n = polys_for(pr, q, m0, j, log_dom, order, pi_locs, log_n, pi_first, tail)
             a = [ea(ea(esc(T[i], x), esc(U[i], x)), esc(M[i], x * x % P)) for i in range(n)]
             b = [es(es(esc(T[i], (P - om) % P), U[i]), esc(M[i], x * (1 + om) % P)) for i in range(n)]
             c = [esc(M[i], om) for i in range(n)]

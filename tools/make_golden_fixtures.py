@@ -65,6 +65,11 @@ def main():
 DEEP = {   # name -> (proof, VK with the public-input locations, key of the circuit in tests/golden/vk_shapes.json)
     "node_3_0_0": ("test_proofs/recursion_layer/node_layer_proof_3_0_0.json", "setup/recursion_layer/vk_node.json", ["recursion", "node"]),
     "compression_1": ("compression_1_proof.json", "compression_1_vk.json", ["compression", "1"]),
+    # NOT reproduced by this structure (no common root of the three-query system, every hypothesis tried): compression mode 2
+    # (compression_2_proof.json, compression_2_for_wrapper_proof.json -- no specialised boolean column, BoundedBoolean gate) and
+    # the base-layer circuits with lookups (basic_circuit_proof_1_0.json).  See DESIGN.md section 5.
+    "compression_1_for_wrapper": ("test_proofs/aux_layer/compression_for_wrapper_proof_1.json", "setup/aux_layer/compression_for_wrapper_vk_1.json",
+                                  ["compression", "1_for_wrapper"]),
 }
 N_DEEP_QUERIES = 6
 
@@ -79,7 +84,8 @@ def deep_fixtures():
         fp = vk["fixed_parameters"]
         pil = fp["public_inputs_locations"]
         par = fp["parameters"]
-        n_perm = par["num_columns_under_copy_permutation"] + (0 if shape_key == ["compression", "2"] else 1)   # + boolean column
+        # + the specialised boolean column, except compression mode 2 (BoundedBoolean gate on general-purpose columns instead)
+        n_perm = par["num_columns_under_copy_permutation"] + (0 if shape_key[1].startswith("2") else 1)
         n_const = par["num_constant_columns"] + fp["extra_constant_polys_for_selectors"]
 
         def order(w, s, s2, qq):
@@ -99,7 +105,7 @@ def deep_fixtures():
             pr = pr[list(pr.keys())[0]]
         log_dom = fx["log_domains"][0]
         qs = []
-        for q in range(N_DEEP_QUERIES):
+        for q in range(min(N_DEEP_QUERIES, len(fx["queries"]))):
             Q = pr["queries_per_fri_repetition"][q]
             pos = r["positions"][q]
             idx = (fx["queries"][q]["leaf_indexes"][0] << 3) + pos
