@@ -37,10 +37,10 @@ Shape make_shape(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
 // openings internally in ORACLE order -- index i: witness columns [0,W), setup columns [W,W+S), stage-2 Ext2 polys, quotient
 // Ext2 polys -- and permutes at the boundary.  Reference order (boojum's verifier walks values_at_z as: variables, witness
 // columns, constants, copy-permutation sigmas, grand product z, partial products, lookup multiplicities, lookup A polys, lookup B,
-// lookup table columns, quotient chunks).  The lookup-free part of this order -- witness leaf, CONSTANTS, SIGMAS, stage 2,
-// quotient, with the setup leaf itself stored sigmas-then-constants -- is pinned hash-free on the reference's golden proofs
-// compression_1_proof.json and node_layer_proof_3_0_0.json (tools/golden_deep.py); the placement of the four lookup blocks is
-// recalled, not confirmed.
+// lookup table columns, quotient chunks).  This order -- with the setup leaf itself stored sigmas, constants, table columns and
+// the multiplicity column last in the witness leaf -- is pinned hash-free on the reference's golden proofs (tools/golden_deep.py,
+// tests/golden/deep_*.json): node_layer_proof_3_0_0, compression modes 1 and 2, and five base-layer circuit types with lookups
+// of width 1, 3 and 4 (basic_circuit_proof_{3,4,8,10,13}_0).
 inline std::vector<uint32_t> opening_positions(const zkgpu_geometry& g, const Shape& sh) {
     std::vector<uint32_t> pos(sh.n_at_z);
     uint32_t p = 0;

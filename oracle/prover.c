@@ -50,8 +50,8 @@ EXPORT uint32_t orc_num_stage2_cols(const zkgpu_geometry *g) { return 2 * n_s2_e
  * h(x) = sum_i phi^i (F_i(x) - F_i(z)) / (x - z) + phi^n (Z(x) - Z(z w)) / (x - z w) + sum_j phi^.. (A_j(x) - A_j(0)) / x
  *        + sum_t phi^.. (w_col_t(x) - pi_t) / (x - w^row_t)
  * F_i in the order of the reference's values_at_z (see the openings section of orc_prove); wl/sl/l2/lq = the four trace-oracle
- * leaves at x (stage-2 and quotient Ext2 polys as adjacent (c0, c1) columns).  Pinned hash-free on golden proofs for lookup-free
- * circuits (tests/golden/deep_*.json). */
+ * leaves at x (stage-2 and quotient Ext2 polys as adjacent (c0, c1) columns).  Pinned hash-free on golden proofs
+ * (tests/golden/deep_*.json): node, compression modes 1 and 2, and base-layer circuits with lookups of width 1, 3 and 4. */
 typedef struct { int kind; uint32_t idx; } open_src; /* kind 0: witness column, 1: setup column, 2: stage-2 Ext2 poly, 3: quotient Ext2 poly */
 static uint32_t opening_sources(const zkgpu_geometry *g, open_src *src) {
     const uint32_t NP = n_perm(g), W = n_wit(g), S = n_setup(g), C = n_chunks(g), E2 = n_s2_ext(g), QD = g->quotient_degree;

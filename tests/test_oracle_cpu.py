@@ -182,10 +182,12 @@ def test_golden_fri_chain(oracle, fixture):
 
 @pytest.mark.parametrize("fixture", sorted(glob.glob(os.path.join(GOLDEN, "deep_*.json"))))
 def test_golden_deep_structure(oracle, fixture):
-    """Reference golden proofs (lookup-free circuits): with phi and z recovered WITHOUT the hash (tools/golden_deep.py), the
-    oracle's DEEP combination of the four trace-oracle leaves of a query -- openings paired in the order of the proof's
-    values_at_z (witness leaf, constants, sigmas, stage 2, quotient), the z*omega opening of the grand product, the public inputs
-    opened at omega^row -- reproduces the value the proof holds in its FRI base oracle, bit for bit."""
+    """Reference golden proofs: with phi and z recovered WITHOUT the hash (tools/golden_deep.py), the oracle's DEEP combination
+    of the four trace-oracle leaves of a query -- openings paired in the order of the proof's values_at_z (variables, plain
+    witness, constants, sigmas, grand product + partial products, lookup multiplicities, lookup A polys and B, lookup table
+    columns, quotient), the z*omega opening of the grand product, the lookup polys opened at 0, the public inputs opened at
+    omega^row -- reproduces the value the proof holds in its FRI base oracle, bit for bit.  Covers lookup-free circuits (node,
+    compression modes 1 and 2) and five base-layer circuit types with lookups of width 1, 3 and 4."""
     from era_zkevm_test_harness_b200 import geometry as G
     fx = json.load(open(fixture))
     assert fx["all_fixture_queries_consistent"]
@@ -194,9 +196,12 @@ def test_golden_deep_structure(oracle, fixture):
     if fx["shape_key"][0] == "compression":
         mode = entry["mode"]
         geo = G.geometry_from_vk(entry, G.COMPRESSION_GATE_ORDER[mode], has_boolean_col=1 if mode == 1 else 0)
+    elif fx["shape_key"][0] == "base":
+        geo = G.geometry_from_vk(entry, G.BASE_LAYER_GATE_ORDER[int(fx["shape_key"][1])])
+        assert geo.lookup_reps > 0 and len(fx["values_at_0"]) == geo.lookup_reps + 1
     else:
         geo = G.geometry_from_vk(entry, G.RECURSION_GATE_ORDER)
-    assert geo.lookup_reps == 0 and len(fx["values_at_z"]) == geo.n_witness + geo.n_setup + geo.n_stage2 // 2 + geo.n_quotient // 2
+    assert len(fx["values_at_z"]) == geo.n_witness + geo.n_setup + geo.n_stage2 // 2 + geo.n_quotient // 2
     for q in fx["queries"]:
         assert len(q["witness"]) == geo.n_witness and len(q["setup"]) == geo.n_setup
         got = oracle.deep_at_point(geo, q["witness"], q["setup"], q["stage_2"], q["quotient"], fx["values_at_z"], fx["values_at_z_omega"][0],

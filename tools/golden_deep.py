@@ -96,18 +96,18 @@ def peval(p, v):
     return r
 
 
-def solve(proof_path, fx_path, order=("w", "s", "2", "q"), pi_locs=None, pi_first=False):
+def solve(proof_path, fx_path, order=("w", "s", "2", "q"), pi_locs=None, pi_first=False, triple=(0, 1, 2)):
     pr = json.load(open(proof_path))
     if "proof_config" not in pr:
         pr = pr[list(pr.keys())[0]]
     fx = json.load(open(fx_path))
     lde = pr["proof_config"]["fri_lde_factor"]
     log_n = fx["log_domains"][0] - (lde.bit_length() - 1)
-    polys, n = build(pr, fx, [0, 1, 2], order, log_n, pi_locs, pi_first)
+    polys, n = build(pr, fx, list(triple), order, log_n, pi_locs, pi_first)
     path = "/tmp/deep_in.bin"
     with open(path, "wb") as f:
         f.write(struct.pack("<3Q", 3, 8, n))
-        for q in (0, 1, 2):
+        for q in triple:
             for j in range(8):
                 for p in polys[(q, j)]:
                     f.write(struct.pack("<%dQ" % (2 * n), *[v for co in p for v in co]))
@@ -119,8 +119,8 @@ def solve(proof_path, fx_path, order=("w", "s", "2", "q"), pi_locs=None, pi_firs
     for hshit in hits:
         j0, j1 = int(hshit[1]), int(hshit[2])
         phi = (int(hshit[6]), int(hshit[7]))
-        a1, b1, c1 = [peval(p, phi) for p in polys[(0, j0)]]
-        a2, b2, c2 = [peval(p, phi) for p in polys[(1, j1)]]
+        a1, b1, c1 = [peval(p, phi) for p in polys[(triple[0], j0)]]
+        a2, b2, c2 = [peval(p, phi) for p in polys[(triple[1], j1)]]
         den = es(em(c2, b1), em(c1, b2))
         if den == ZERO:
             continue

@@ -1,4 +1,11 @@
 # Hash-free recovery of every FRI folding challenge and of each query's leaf index in every FRI oracle from a golden proof.
+#
+# Rotation ambiguity: folding only sees ratios c/x, so the chain (x, c_k) and the chain (zeta*x, c_k * zeta^(2^..)) for a domain
+# element zeta = omega^t explain the same leaves as long as (i) the final polynomial is invariant -- always true for the ONE-monomial
+# final polynomial of the compression layer, never for the 8 monomials of the base/recursion layer -- and (ii) no query leaves its
+# leaf (brev(leaf index) + t stays inside [0, leaves) at every level).  With 100 queries (ii) forces t = 0; with the 9 queries of
+# compression mode 2 about a hundred rotations survive and this script returns one of them.  The DEEP relation sees x itself and
+# picks the true one (tools/make_golden_fixtures.py: rotation_candidates / rotate_chain; fixture key rotation_resolved_by_deep).
 import json, sys, itertools
 P=(1<<64)-(1<<32)+1
 G=0x185629dcda58878c
