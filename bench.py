@@ -36,49 +36,101 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline (oracle port)
-def cpu_baseline(log_n_full, log_n_sample):
-    """Times the CPU restatement (oracle/prover.c, OpenMP on all host cores) on a bounded sample: the same MainVM geometry
-    and proof config on a shorter trace, then scales by (N log N) to trace 2^20.  kind = "port": the reference's Rust prover
-    (boojum) cannot be built in this image (no Rust toolchain, un-vendored git dependencies)."""
-    from era_zkevm_test_harness_b200 import geometry as G
-    from era_zkevm_test_harness_b200 import prover_utils as PU
+WORKLOAD = "MainVM-shaped base-layer circuit (W156/S2 58/Q16/S167, 11 gates incl. flattened Poseidon2, lookup 3x8), trace 2^{log_n}, lde 2, cap 16, 100 queries"
+
+
+def _geometry_module():
+    """geometry.py alone (ctypes structs, pure Python): the CPU arm must not import the package, whose __init__ pulls in torch
+    and the binding of libzkgpu.so."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zk_geometry_only", os.path.join(ROOT, "era_zkevm_test_harness_b200", "geometry.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _oracle_with_all_cores():
+    """liboracle.so with its OpenMP team set to every core this process may run on -- explicitly, because
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would serialise the CPU prover."""
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     from tests import oracle_lib
     oracle = oracle_lib.load()
-    geo = G.mainvm_like_geometry(log_n_sample)
-    cfg = G.base_layer_proof_config(log_n_sample)
-    wit, setup = PU.synth_trace(geo, seed=1)
+    return oracle, oracle.set_threads(cores)
+
+
+def cpu_prove_once(log_n, seed=1):
+    """One whole proof of the MainVM-shaped circuit at trace 2^log_n by the CPU restatement (oracle/prover.c, OpenMP), on a trace
+    made by oracle/synth.c.  Nothing of the product (libzkgpu.so, torch) is loaded on this path.  kind = "port": the reference's
+    Rust prover (boojum) cannot be built in this image (no Rust toolchain, un-vendored git dependencies)."""
+    G = _geometry_module()
+    oracle, threads = _oracle_with_all_cores()
+    geo = G.mainvm_like_geometry(log_n)
+    cfg = G.base_layer_proof_config(log_n)
+    wit, setup = oracle.synth_trace(geo, seed=seed)
     t0 = time.time()
     proof = oracle.prove(geo, cfg, wit, setup)
-    dt = time.time() - t0
+    return time.time() - t0, threads, int(proof.size)
+
+
+def cpu_baseline(log_n_full, log_n_sample):
+    """Bounded sample for the GPU arm's line: one whole CPU proof of the same geometry and proof config on a SHORTER trace
+    (2^log_n_sample rows, ~10-30 s), reported both as measured and scaled by N log N to the metric's trace length.  The
+    un-extrapolated number is what `bench.py --impl reference` measures: one full 2^20 proof."""
+    dt, threads, n_u64 = cpu_prove_once(log_n_sample)
     scale = ((1 << log_n_full) * log_n_full) / ((1 << log_n_sample) * log_n_sample)
-    cores = len(os.sched_getaffinity(0))
-    return {"value": 1.0 / (dt * scale), "unit": "proofs/s", "cores": cores, "kind": "port",
-            "sample": f"one full proof (oracle/prover.c, OpenMP) of the MainVM geometry at trace 2^{log_n_sample} took {dt:.2f} s; "
-                      f"scaled by N*log2(N) x{scale:.0f} to trace 2^{log_n_full}",
-            "sample_seconds": dt, "proof_u64": int(proof.size)}
+    return {"value": 1.0 / (dt * scale), "unit": "proofs/s", "cores": threads, "kind": "port", "extrapolated": log_n_sample != log_n_full,
+            "sample": f"one whole proof (oracle/prover.c, OpenMP x{threads}) of the MainVM geometry at trace 2^{log_n_sample} took {dt:.2f} s"
+                      + (f"; scaled by N*log2(N) x{scale:.1f} to trace 2^{log_n_full}" if log_n_sample != log_n_full else ""),
+            "sample_seconds": dt, "sample_value_unscaled": 1.0 / dt, "sample_log_n": log_n_sample, "proof_u64": n_u64}
 
 
 def run_reference(args):
+    """CPU arm: ONE full-size proof (trace 2^log_n, the GPU arm's exact geometry and proof config) by the CPU restatement on all
+    host cores -- measured, not extrapolated.  A full proof takes minutes on the host, so --steps/--warmup are not repeated:
+    steps_measured = 1, warmup_measured = 0 (the page cache and the OpenMP team are warmed by the trace generator).  Under
+    torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = None
-    times = []
-    for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args.log_n, args.cpu_log_n)
-        if i >= args.warmup:
-            times.append(1.0 / cb["value"])
-    sec = sum(times) / len(times)
+    sec, threads, n_u64 = cpu_prove_once(args.log_n)
     value = 1.0 / sec
-    cb["value"] = value
+    cb = {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "extrapolated": False,
+          "sample": f"one whole proof (oracle/prover.c, OpenMP x{threads}) of the MainVM geometry at trace 2^{args.log_n} took {sec:.1f} s",
+          "sample_seconds": sec, "proof_u64": n_u64}
     print(json.dumps({
         "impl": "reference", "metric": "base_layer_proofs_per_sec_trace_2^20", "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64", "data": "synthetic",
-        "config": {"workload": f"MainVM-shaped base-layer circuit (W156/S2 58/Q16/S167), trace 2^{args.log_n}, lde 2, cap 16, 100 queries",
-                   "note": "CPU restatement of the prover (oracle port, not boojum) on all host cores; bounded sample scaled to 2^20"},
+        "steps": args.steps, "warmup": args.warmup, "steps_measured": 1, "warmup_measured": 0, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(log_n=args.log_n) + "; one instance per GPU per step",
+                   "note": "CPU restatement of the prover (oracle port, not boojum) on all host cores of rank 0; one full-size proof, no extrapolation"},
         "cpu_baseline": cb, "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def ntt_traffic_from_profiles():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the two launches (pass A, pass B) of one forward coset NTT batch of 156
+    columns x 2^20, read from the newest committed `ncu --set full` export profiles/r*_prims_raw.csv (tools/ncu_capture.sh over
+    tools/profile_kernels.py primitives: the same ctx.ntt_forward call this bench times).  Returns (bytes, source) or (None, why)."""
+    import csv
+    import glob
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prims_raw.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            idx = {h: i for i, h in enumerate(rows[0])}
+            units = rows[1]
+            fwd = [r for r in rows[2:] if "ntt1024" in r[idx["Kernel Name"]]][:2]      # first captured batch: forward pass A + pass B
+            if len(fwd) < 2 or any(r[idx["Grid Size"]].replace(" ", "") != "(128,156,1)" for r in fwd):
+                continue
+            total = 0.0
+            for r in fwd:
+                for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(r[idx[key]].replace(",", "")) * scale[units[idx[key]]]
+            return total, os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, "no profiles/r*_prims_raw.csv with an ntt1024 batch of 156 columns"
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -265,11 +317,9 @@ def run_ours(args):
         ntt_ms = e0.elapsed_time(e1) / reps
         alg_bytes = 16.0 * n * W                      # 16*n bytes per size-n NTT per column
         achieved = alg_bytes / (ntt_ms * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of the two launches of one batch, from the committed ncu capture of this
-        # same call (profiles/r01_d_prims_raw.csv: pass A 1.371 + 1.270 GB, pass B 1.309 + 1.250 GB)
-        traffic = 5.200e9 if (log_n == 20 and W == 156) else None
+        traffic, traffic_src = ntt_traffic_from_profiles() if (log_n == 20 and W == 156) else (None, "not the captured shape")
         roof = {"bound": "hbm", "kernel": "zk::ntt1024_kernel (pass A strided columns + pass B rows = 2 launches per batched 2^20 coset NTT)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_transform_batch": alg_bytes, "ms_per_transform_batch": ntt_ms,
                 "frac_of_nominal_8TBps": achieved / 8000.0,
                 "note": "integer-issue-bound, not HBM-bound: no 64-bit multiplier on sm_100a (ncu: alu pipe 67-75 % busy, dram 18-27 %)"}
@@ -299,8 +349,7 @@ def run_ours(args):
             "metric": "base_layer_proofs_per_sec_trace_2^20", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"MainVM-shaped base-layer circuit (W156/S2 58/Q16/S167, 11 gates incl. flattened Poseidon2, lookup 3x8), "
-                                   f"trace 2^{log_n}, lde 2, cap 16, 100 queries; one instance per GPU per step",
+            "config": {"workload": WORKLOAD.format(log_n=log_n) + "; one instance per GPU per step",
                        "l2": "inputs larger than L2 (1.3 GB witness, 13 GB setup cosets per proof)", "proof_bytes": n_proof * 8,
                        "proof_verified_by_cpu_verifier": verified},
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": int(wit.nbytes) * world, "d2h_bytes_per_step": n_proof * 8 * world,

@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzkgpu.so")
+LIB_PATH = os.environ.get("ZKGPU_LIB") or os.path.join(_HERE, "libzkgpu.so")   # ZKGPU_LIB: a build variant for A/B measurements
 
 u64 = ctypes.c_uint64
 u64p = ctypes.c_void_p  # device or host pointer passed as an integer address

@@ -6,10 +6,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libzkgpu.so")
+LIB = os.environ.get("ZKGPU_BUILD_OUT") or os.path.join(HERE, "libzkgpu.so")   # variants for A/B runs: ZKGPU_BUILD_OUT, ZKGPU_BUILD_FLAGS
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"]
+         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-ccbin", "/usr/bin/g++"] + os.environ.get("ZKGPU_BUILD_FLAGS", "").split()
 
 
 def sources():
@@ -29,9 +29,10 @@ def build(force=False, verbose=False):
         return LIB
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = os.path.join(HERE, "build" if LIB.endswith("libzkgpu.so") else "build_" + os.path.basename(LIB))
+    os.makedirs(bdir, exist_ok=True)
     for src in sources():
-        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(bdir, os.path.basename(src)[:-3] + ".o")
         cmd = [NVCC] + [f for f in FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")

@@ -51,6 +51,7 @@ GL_HD uint32_t gate_width(uint32_t kind) {
         case ZKGPU_GATE_FMA_EXT: return 8;
         case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 5;
         case ZKGPU_GATE_BOUNDED_BOOLEAN: return 1;
+        case ZKGPU_GATE_BOOLEAN_ALL: return 1;
         case ZKGPU_GATE_MATMUL12_EXTERNAL: return 24;
         case ZKGPU_GATE_MATMUL12_INNER: return 24;
         case ZKGPU_GATE_NONLINEARITY7: return 2;
@@ -74,6 +75,7 @@ GL_HD uint32_t gate_relations(uint32_t kind) {
         case ZKGPU_GATE_FMA_EXT: return 2;
         case ZKGPU_GATE_U32_TRI_ADD_CARRY: return 1;
         case ZKGPU_GATE_BOUNDED_BOOLEAN: return 1;
+        case ZKGPU_GATE_BOOLEAN_ALL: return 1;
         case ZKGPU_GATE_MATMUL12_EXTERNAL: return 12;
         case ZKGPU_GATE_MATMUL12_INNER: return 12;
         case ZKGPU_GATE_NONLINEARITY7: return 1;
@@ -203,6 +205,7 @@ GL_HD void eval_gate(const zkgpu_gate& g, const zkgpu_geometry& geo, const uint6
             }
             break;
         case ZKGPU_GATE_BOUNDED_BOOLEAN:
+        case ZKGPU_GATE_BOOLEAN_ALL:
             for (uint32_t t = 0; t < inst; t++) {
                 F x = acc(t);
                 sink(f_sub(f_mul(x, x), x));

@@ -256,6 +256,7 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t setup_seed, uint64_t s
                     }
                     break;
                 case ZKGPU_GATE_BOUNDED_BOOLEAN:
+                case ZKGPU_GATE_BOOLEAN_ALL:
                     for (uint32_t t = 0; t < inst; t++) v[t] = rng.next() & 1;
                     break;
                 case ZKGPU_GATE_MATMUL12_EXTERNAL:

@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
                 }
                 break;
             case ZKGPU_GATE_BOUNDED_BOOLEAN:
+            case ZKGPU_GATE_BOOLEAN_ALL:
 #pragma unroll 1
                 for (uint32_t t = 0; t < inst; t++) {
                     const uint64_t x = w[(size_t)t * cw];

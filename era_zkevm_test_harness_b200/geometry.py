@@ -19,7 +19,7 @@ MAX_FRI = 16
 (GATE_NOP, GATE_CONSTANTS_ALLOCATOR, GATE_FMA, GATE_REDUCTION4, GATE_SELECTION, GATE_PARALLEL_SELECTION4, GATE_ZERO_CHECK,
  GATE_UINTX_ADD, GATE_DOT_PRODUCT4, GATE_U8X4_FMA, GATE_POSEIDON2_FLATTENED, GATE_FMA_EXT, GATE_U32_TRI_ADD_CARRY,
  GATE_BOUNDED_BOOLEAN, GATE_MATMUL12_EXTERNAL, GATE_MATMUL12_INNER, GATE_NONLINEARITY7, GATE_CONDITIONAL_SWAP4,
- GATE_ZERO_CHECK_WITNESS) = range(19)
+ GATE_ZERO_CHECK_WITNESS, GATE_BOOLEAN_ALL) = range(20)
 
 GATE_NAMES = {
     "ConstantsAllocator": GATE_CONSTANTS_ALLOCATOR, "FmaBaseNoConst": GATE_FMA, "Reduction4": GATE_REDUCTION4,
@@ -30,6 +30,7 @@ GATE_NAMES = {
     # compression circuits (aux_layer/compression_modes/mode_{1..4}.rs)
     "BoundedBoolean": GATE_BOUNDED_BOOLEAN, "MatMul12External": GATE_MATMUL12_EXTERNAL, "MatMul12Inner": GATE_MATMUL12_INNER,
     "Nonlinearity7": GATE_NONLINEARITY7, "ConditionalSwap4": GATE_CONDITIONAL_SWAP4, "ZeroCheckWitness": GATE_ZERO_CHECK_WITNESS,
+    "BooleanAllColumns": GATE_BOOLEAN_ALL,  # EIP-4844: BooleanConstraintGate on general-purpose columns
 }
 
 # gate_idx -> gate name per verification key, derived in SURVEY.md section 8a by matching each VK's
@@ -64,6 +65,13 @@ COMPRESSION_GATE_ORDER = {
 }
 RECURSION_GATE_ORDER = ["ConstantsAllocator", "Poseidon2Flattened", "ZeroCheck", "FmaBaseNoConst", "FmaExt", "UIntXAdd", "Selection",
                         "ParallelSelection4", "PublicInput", "Reduction4"]
+
+# EIP-4844 circuit (circuit_definitions/src/circuit_definitions/eip4844/mod.rs:43-112, VK setup/aux_layer/eip4844_vk.json):
+# 60 copy columns, 8 constant columns, lookup 3x20, NO specialised boolean column -- BooleanConstraintGate sits on the
+# general-purpose columns (one instance per column); (num_constants, degree) per gate_idx match the VK:
+# (8,1) (0,0) (2,3) (4,2) (0,2) (1,2) (0,2) (0,2).  UIntXAddGate<32>/<16> collapse into one entry like everywhere else.
+EIP4844_GATE_ORDER = ["ConstantsAllocator", "PublicInput", "FmaBaseNoConst", "Reduction4", "BooleanAllColumns", "UIntXAdd", "Selection",
+                      "DotProduct4"]
 
 BASE_LAYER_CIRCUIT_NAMES = {
     1: "MainVM", 2: "CodeDecommittmentsSorter", 3: "CodeDecommitter", 4: "LogDemuxer", 5: "KeccakRoundFunction", 6: "Sha256RoundFunction",
@@ -155,6 +163,11 @@ def make_proof_config(log_n, fri_lde_factor=2, merkle_tree_cap_size=16, security
     for i, s in enumerate(sched):
         cfg.fri_schedule[i] = s
     return cfg
+
+
+def eip4844_proof_config(log_n=20):
+    """circuit_definitions/src/lib.rs:49-57 `eip4844_proof_config()`: the base-layer constants."""
+    return base_layer_proof_config(log_n)
 
 
 def base_layer_proof_config(log_n=20):
@@ -294,6 +307,9 @@ def circuit_geometries_from_fixture(fixture):
         yield f"base_{t}_{entry['variant']}", geometry_from_vk(entry, BASE_LAYER_GATE_ORDER[int(t)]), entry
     for key, entry in fixture["recursion"].items():
         yield f"recursion_{key}", geometry_from_vk(entry, RECURSION_GATE_ORDER), entry
+    if "eip4844" in fixture.get("aux", {}):
+        entry = fixture["aux"]["eip4844"]
+        yield "aux_eip4844", geometry_from_vk(entry, EIP4844_GATE_ORDER, has_boolean_col=0), entry
 
 
 def compression_geometries_from_fixture(fixture):

@@ -101,6 +101,7 @@ enum {
     ZKGPU_GATE_NONLINEARITY7,         /* y - (x + k)^7, one gate constant (deg 7)                         SimpleNonlinearityGate<7> */
     ZKGPU_GATE_CONDITIONAL_SWAP4,     /* s*(b_i-a_i)+a_i-ra_i, s*(a_i-b_i)+b_i-rb_i, i<4 (deg 2)             ConditionalSwapGate<4> */
     ZKGPU_GATE_ZERO_CHECK_WITNESS,    /* ZeroCheckGate with the inverse in a plain witness column (use_witness = true)        */
+    ZKGPU_GATE_BOOLEAN_ALL,           /* x^2 - x on EVERY copy column (deg 2): BooleanConstraintGate on general-purpose columns (eip4844/mod.rs:95-98) */
     ZKGPU_GATE_KINDS
 };
 

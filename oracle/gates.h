@@ -9,11 +9,11 @@
 #include "gl64.h"
 
 static inline uint32_t og_width(uint32_t kind) {
-    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8, 5, 1, 24, 24, 2, 17, 2};
+    static const uint32_t W[ZKGPU_GATE_KINDS] = {0, 1, 4, 5, 4, 13, 3, 5, 9, 26, 130, 8, 5, 1, 24, 24, 2, 17, 2, 1};
     return kind < ZKGPU_GATE_KINDS ? W[kind] : 0;
 }
 static inline uint32_t og_relations(uint32_t kind) {
-    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2, 1, 1, 12, 12, 1, 8, 2};
+    static const uint32_t R[ZKGPU_GATE_KINDS] = {0, 1, 1, 1, 1, 4, 2, 2, 1, 1, 118, 2, 1, 1, 12, 12, 1, 8, 2, 1};
     return kind < ZKGPU_GATE_KINDS ? R[kind] : 0;
 }
 /* gate cells: the copy columns followed by the plain witness columns (include/zkgpu.h: n_witness_plain) */
@@ -58,7 +58,7 @@ static inline uint64_t og_pow7(uint64_t x) { return gl_mul(gl_mul(gl_sqr(gl_sqr(
 
 /* writes the relation values of gate g at one point into out[], returns how many.  v = gate CELL values (copy columns,
  * then plain witness columns), k = the gate's constants (constant columns starting at path_len), rc = Poseidon2 round constants. */
-static uint32_t og_eval_gate(const zkgpu_gate *g, const zkgpu_geometry *geo, const uint64_t *v, const uint64_t *k, const uint64_t *rc, uint64_t *out) {
+static __attribute__((unused)) uint32_t og_eval_gate(const zkgpu_gate *g, const zkgpu_geometry *geo, const uint64_t *v, const uint64_t *k, const uint64_t *rc, uint64_t *out) {
     uint32_t inst = og_instances(g, geo), n = 0;
     const uint32_t n_copy = geo->n_copy;
     switch (g->kind) {
@@ -118,6 +118,7 @@ static uint32_t og_eval_gate(const zkgpu_gate *g, const zkgpu_geometry *geo, con
         }
         break;
     case ZKGPU_GATE_BOUNDED_BOOLEAN:
+    case ZKGPU_GATE_BOOLEAN_ALL:
         for (uint32_t t = 0; t < inst; t++) out[n++] = gl_sub(gl_sqr(v[t]), v[t]);
         break;
     case ZKGPU_GATE_MATMUL12_EXTERNAL:

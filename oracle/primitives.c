@@ -24,6 +24,14 @@
 
 #define EXPORT __attribute__((visibility("default")))
 
+/* OpenMP team size of every orc_* call; bench.py sets it explicitly (torchrun exports OMP_NUM_THREADS=1). Returns the team size. */
+#ifdef _OPENMP
+#include <omp.h>
+EXPORT int orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+EXPORT int orc_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* ------------------------------------------------------------------ field vectors (for parity tests) */
 EXPORT void orc_gl_mul_vec(const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = gl_mul(a[i], b[i]); }
 EXPORT void orc_gl_add_vec(const uint64_t *a, const uint64_t *b, uint64_t *o, size_t n) { for (size_t i = 0; i < n; i++) o[i] = gl_add(a[i], b[i]); }

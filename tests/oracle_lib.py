@@ -52,6 +52,8 @@ class Oracle:
         for nm in ("orc_num_witness_cols", "orc_num_setup_cols", "orc_num_stage2_cols"):
             getattr(L, nm).restype = ctypes.c_uint32; getattr(L, nm).argtypes = [vp]
         L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
+        L.orc_set_threads.restype = ci; L.orc_set_threads.argtypes = [ci]
+        L.orc_synth_trace.restype = ci; L.orc_synth_trace.argtypes = [vp, c_u64, c_u64, ci, vp, vp]
 
     @staticmethod
     def _p(a):
@@ -163,6 +165,21 @@ class Oracle:
         w = self.lib.orc_prove(ctypes.byref(geo), ctypes.byref(cfg), self._p(wit_cols), self._p(setup_cols), self._p(proof), n)
         assert w == n, (w, n)
         return proof
+
+    def set_threads(self, n):
+        return int(self.lib.orc_set_threads(int(n)))
+
+    def synth_trace(self, geo, seed=0, witness_seed=None):
+        """Synthetic satisfying trace (oracle/synth.c): (witness_cols [W,n], setup_cols [S,n]), the generator of
+        era_zkevm_test_harness_b200.prover_utils.synth_trace restated in C without the product library."""
+        n = 1 << geo.log_n
+        wit = np.empty((int(self.lib.orc_num_witness_cols(ctypes.byref(geo))), n), dtype=np.uint64)
+        setup = np.empty((int(self.lib.orc_num_setup_cols(ctypes.byref(geo))), n), dtype=np.uint64)
+        if witness_seed is None:
+            self.lib.orc_synth_trace(ctypes.byref(geo), seed, seed, 0, self._p(wit), self._p(setup))
+        else:
+            self.lib.orc_synth_trace(ctypes.byref(geo), seed, witness_seed, 1, self._p(wit), self._p(setup))
+        return wit, setup
 
     def deep_at_point(self, geo, wl, sl, l2, lq, at_z, at_zw, at_0, pi, x, z, phi):
         """DEEP combination at one LDE point (oracle/prover.c deep_point): leaves of the four trace oracles at x, openings in

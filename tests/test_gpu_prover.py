@@ -76,6 +76,47 @@ def test_full_size_mainvm_proof_verifies(gpu):
     sd.close()
 
 
+def test_full_size_mainvm_proof_equals_oracle(gpu):
+    """The headline configuration end to end, every u64: MainVM geometry, trace 2^20, lde 2, cap 16, 100 queries, trace seed 1.
+    The CPU oracle's proof of exactly this input is cached in tests/golden/oracle_proof_mainvm_2pow20_seed1.npy
+    (tools/make_oracle_fullsize_fixture.py: ~8 min of oracle/prover.c on 8 cores); the CUDA prover must reproduce all 93 069
+    words -- this is the only size that runs ntt1024_kernel, the 17 GiB arena, size_t-wide indices and the staged upload."""
+    import os
+    ref = np.load(os.path.join(os.path.dirname(__file__), "golden", "oracle_proof_mainvm_2pow20_seed1.npy"))
+    geo = G.mainvm_like_geometry(20)
+    cfg = G.base_layer_proof_config(20)
+    wit, setup = PU.synth_trace(geo, seed=1, pinned=True)
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    proof = PU.prove_circuit(gpu, sd, wit)
+    assert proof.size == ref.size
+    assert _first_diff(proof, ref) is None, f"first differing u64 at {_first_diff(proof, ref)}"
+    # the staged (double-buffered upload) entry point and the device-resident one give the same bytes
+    PU.stage_witness(gpu, sd, wit, 0)
+    assert (PU.prove_staged(gpu, sd, 0) == ref).all()
+    d_wit = torch.from_numpy(wit.view(np.int64)).to(gpu.device)
+    assert (PU.prove_circuit(gpu, sd, d_wit) == ref).all()
+    sd.close()
+
+
+def test_compression_mode_1_reference_size_equals_oracle(gpu):
+    """Compression mode 1 at its reference size (2^16 rows x LDE 32, cap 16, 16 queries; plain witness columns, FRI schedule
+    3,3,3,3,3,1): every u64 of the CUDA proof equals the cached oracle proof (tests/golden/oracle_proof_compression_1_seed1.npy)."""
+    import json
+    import os
+    golden = os.path.join(os.path.dirname(__file__), "golden")
+    ref = np.load(os.path.join(golden, "oracle_proof_compression_1_seed1.npy"))
+    fixture = json.load(open(os.path.join(golden, "vk_shapes.json")))
+    geo, cfg = [(g, c) for k, g, c, _ in G.compression_geometries_from_fixture(fixture) if k == "compression_1"][0]
+    wit, setup = PU.synth_trace(geo, seed=1)
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    proof = PU.prove_circuit(gpu, sd, wit)
+    assert proof.size == ref.size
+    assert _first_diff(proof, ref) is None, f"first differing u64 at {_first_diff(proof, ref)}"
+    ok, msg = PU.verify_proof(geo, cfg, sd.vk_cap, proof)
+    assert ok, msg
+    sd.close()
+
+
 def test_prove_from_variables_matches_column_path(gpu, oracle):
     """the reference's hand-off: variable values + per-type variable maps (DenseVariablesCopyHint) instead of materialised
     columns.  A random assignment of cells to variables (with repeated variables = copy constraints and placeholders for zero

@@ -124,3 +124,27 @@ def test_compression_mode_proof_configs(oracle, mode, queries):
     proof = oracle.prove(geo, cfg, wit, setup)
     ok, msg = PU.verify_proof(geo, cfg, oracle.setup_cap(geo, cfg, setup), proof)
     assert ok, msg
+
+
+@pytest.mark.parametrize("kind", ["mainvm", "small_nolookup", "compression_1", "compression_4", "storage_application"])
+def test_oracle_trace_generator_matches_product_generator(oracle, kind):
+    """oracle/synth.c (used by bench.py's CPU reference arm, which must not load libzkgpu.so) and the product's host-side
+    zkgpu_synth_trace produce the same satisfying trace, bit for bit, for both seeding modes."""
+    import json, os
+    fixture = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
+    if kind == "mainvm":
+        geo = G.mainvm_like_geometry(9)
+    elif kind == "small_nolookup":
+        geo = G.small_test_geometry(log_n=7, lookup=False)
+    elif kind == "storage_application":
+        geo = [g for k, g, _ in G.circuit_geometries_from_fixture(fixture) if k.startswith("base_10_")][0]
+        geo.log_n, geo.table_len = 8, min(geo.table_len, 1 << 8)
+    else:
+        geo = [g for k, g, _c, _ in G.compression_geometries_from_fixture(fixture) if k == kind][0]
+        geo.log_n = 7
+    for i in range(geo.n_public_inputs):
+        geo.pi_row[i] = 5
+    for seed, wseed in ((3, None), (3, 11)):
+        w0, s0 = PU.synth_trace(geo, seed=seed, witness_seed=wseed)
+        w1, s1 = oracle.synth_trace(geo, seed=seed, witness_seed=wseed)
+        assert np.array_equal(w0, w1) and np.array_equal(s0, s1)

@@ -38,7 +38,11 @@ def proof_shape(path):
 
 
 def main():
-    out = {"base": {}, "recursion": {}, "compression": {}}
+    out = {"base": {}, "recursion": {}, "compression": {}, "aux": {}}
+    # EIP-4844 circuit (prove_eip4844_circuit, src/prover_utils.rs:763-808): a VK only, the reference holds no proof of it
+    name, vk = inner(json.load(open(f"{REF}/setup/aux_layer/eip4844_vk.json")))
+    out["aux"]["eip4844"] = {"variant": name or "EIP4844", "fixed_parameters": vk["fixed_parameters"],
+                             "setup_merkle_tree_cap": vk["setup_merkle_tree_cap"], "proof_shapes": []}
     for t in range(1, 14):
         name, vk = inner(json.load(open(f"{REF}/setup/base_layer/vk_{t}.json")))
         proofs = sorted(glob.glob(f"{REF}/test_proofs/base_layer/basic_circuit_proof_{t}_*.json"))
