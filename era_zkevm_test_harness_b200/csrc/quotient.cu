@@ -18,6 +18,12 @@
 #include "quotient.cuh"
 #include "dot.cuh"
 
+#ifndef ZK_PERM_UNROLL
+#define ZK_PERM_UNROLL 1
+#endif
+#define ZK_PRAGMA_(x) _Pragma(#x)
+#define ZK_UNROLL(n) ZK_PRAGMA_(unroll n)
+
 namespace zk {
 
 __device__ __forceinline__ uint64_t selector(const uint64_t* __restrict__ kc, size_t cs, uint32_t path_len, uint32_t path_bits) {
@@ -30,14 +36,67 @@ __device__ __forceinline__ uint64_t selector(const uint64_t* __restrict__ kc, si
 }
 
 // ------------------------------------------------------------------------------------------------ general-purpose gates
-__global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_constant__ QuotParams p) {
+// One CTA = QG_P adjacent points of the coset.  The gate cells of those points (copy columns, then plain witness columns) and
+// the constant columns are staged ONCE in shared memory -- one 256-byte TMA bulk copy (cp.async.bulk, 16-byte units) per column
+// onto an mbarrier -- and every gate kind reads them from there: the first version walked the columns in global memory once per
+// gate kind and pulled 6.2 GB per coset through HBM for 1.1 GB of columns (profiles/r01_m_summary.txt).  The QG_SPLIT warps of
+// the CTA take the instances t = warp, warp + QG_SPLIT, ... of every gate for the same 32 points; their partial alpha-weighted
+// sums are added at the end (exact field additions, so the split does not change a bit of the result).
+constexpr int QG_P = 32;   // 2 warps: measured 15.9 ms per proof against 17.6 ms with 4 (each warp repeats the selector and loop set-up)
+#ifndef ZK_QG_SPLIT
+#define ZK_QG_SPLIT 2
+#endif
+constexpr int QG_SPLIT = ZK_QG_SPLIT;
+static size_t quotient_gates_smem(const zkgpu_geometry& g) {
+    return ((size_t)(g.n_copy + g.n_witness_plain + g.n_const_cols) * QG_P + 2 * QG_SPLIT * QG_P) * sizeof(uint64_t);
+}
+__global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_kernel(const __grid_constant__ QuotParams p) {
+    extern __shared__ __align__(128) uint64_t qg_smem[];
+    __shared__ __align__(8) uint64_t qg_bar;
     const size_t N = (size_t)1 << p.g.log_n;
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    const uint64_t* __restrict__ w = p.wit + j;
-    const uint64_t* __restrict__ kc = p.setup + (size_t)p.NP * p.cs_s + j;
+    const uint32_t n_copy = p.g.n_copy, n_cells = p.g.n_copy + p.g.n_witness_plain, n_rows = n_cells + p.g.n_const_cols;
+    uint64_t* tile = qg_smem;                               // [n_cells][QG_P]
+    uint64_t* ktile = qg_smem + (size_t)n_cells * QG_P;      // [n_const_cols][QG_P]
+    uint64_t* red = qg_smem + (size_t)n_rows * QG_P;         // [2][QG_SPLIT][QG_P]
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t j0 = (size_t)blockIdx.x * QG_P;
+    const uint32_t npts = (uint32_t)(N - j0 < QG_P ? N - j0 : QG_P);
+    auto row_src = [&](uint32_t r) -> const uint64_t* {
+        if (r < n_copy) return p.wit + (size_t)r * p.cs_w + j0;
+        if (r < n_cells) return p.wit + (size_t)(p.NP + r - n_copy) * p.cs_w + j0;          // plain witness columns start at NP
+        return p.setup + (size_t)(p.NP + r - n_cells) * p.cs_s + j0;                          // constant columns
+    };
+    const bool bulk = npts == QG_P && ((reinterpret_cast<uintptr_t>(p.wit) | reinterpret_cast<uintptr_t>(p.setup)) & 15) == 0 &&
+                      ((p.cs_w | p.cs_s) & 1) == 0;
+    if (bulk) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&qg_bar);
+        if (tid == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n_rows * QG_P * 8u) : "memory");
+        for (uint32_t r = tid; r < n_rows; r += 32 * QG_SPLIT) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(qg_smem + (size_t)r * QG_P);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(row_src(r)), "r"(QG_P * 8u), "r"(bar) : "memory");
+        }
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+    } else {   // short or unaligned tiles (parity-test sizes): plain loads
+        for (uint32_t i = tid; i < n_rows * QG_P; i += 32 * QG_SPLIT) {
+            const uint32_t r = i / QG_P, c = i % QG_P;
+            qg_smem[i] = c < npts ? row_src(r)[c] : 0;
+        }
+        __syncthreads();
+    }
+    const uint64_t* __restrict__ w = tile + lane;
+    const uint64_t* __restrict__ kc = ktile + lane;
     const ulonglong2* __restrict__ apow = reinterpret_cast<const ulonglong2*>(p.apow);
-    const size_t cw = p.cs_w, cs = p.cs_s;
+    constexpr size_t cw = QG_P, cs = QG_P;
     gl::e2 acc = gl::make2(0, 0);
 
 #pragma unroll 1
@@ -52,12 +111,12 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
         switch (gt.kind) {
             case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) dote_add(d, gl::sub(w[(size_t)t * cw], gk[(size_t)t * cs]), ap[t]);
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) dote_add(d, gl::sub(w[(size_t)t * cw], gk[(size_t)t * cs]), ap[t]);
                 break;
             case ZKGPU_GATE_FMA: {
                 const uint64_t k0 = gk[0], k1 = gk[cs];
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
                     uint64_t r = gl::sub(gl::add(gl::mul(gl::mul(k0, x[0]), x[cw]), gl::mul(k1, x[2 * cw])), x[3 * cw]);
                     dote_add(d, r, ap[t]);
@@ -66,7 +125,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_REDUCTION4: {
                 const uint64_t k0 = gk[0], k1 = gk[cs], k2 = gk[2 * cs], k3 = gk[3 * cs];
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t s = gl::add(gl::add(gl::mul(k0, x[0]), gl::mul(k1, x[cw])), gl::add(gl::mul(k2, x[2 * cw]), gl::mul(k3, x[3 * cw])));
                     dote_add(d, gl::sub(s, x[4 * cw]), ap[t]);
@@ -74,7 +133,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             } break;
             case ZKGPU_GATE_SELECTION:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
                     uint64_t b = x[2 * cw];
                     // s*a + (1-s)*b - out = s*(a - b) + b - out
@@ -83,7 +142,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
                 break;
             case ZKGPU_GATE_PARALLEL_SELECTION4:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(13 * t) * cw;
                     const uint64_t s = x[0];
 #pragma unroll 1
@@ -96,7 +155,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
                 break;
             case ZKGPU_GATE_ZERO_CHECK:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(3 * t) * cw;
                     uint64_t xv = x[0], zf = x[2 * cw];
                     dote_add(d, gl::sub(gl::mul(xv, x[cw]), gl::sub(1, zf)), ap[2 * t]);
@@ -106,7 +165,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_UINTX_ADD: {
                 const uint64_t k0 = gk[0];
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t co = x[4 * cw];
                     uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
@@ -117,7 +176,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             } break;
             case ZKGPU_GATE_U32_TRI_ADD_CARRY:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
                     dote_add(d, gl::sub(lhs, gl::add(x[3 * cw], gl::mul_pow2(x[4 * cw], 32))), ap[t]);
@@ -126,7 +185,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_BOUNDED_BOOLEAN:
             case ZKGPU_GATE_BOOLEAN_ALL:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t x = w[(size_t)t * cw];
                     dote_add(d, gl::sub(gl::sqr(x), x), ap[t]);
                 }
@@ -134,7 +193,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_MATMUL12_EXTERNAL:
             case ZKGPU_GATE_MATMUL12_INNER:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(24 * t) * cw;
                     uint64_t s[12];
 #pragma unroll
@@ -148,14 +207,14 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_NONLINEARITY7: {
                 const uint64_t k0 = gk[0];
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(2 * t) * cw;
                     dote_add(d, gl::sub(x[cw], glx::canon(glx::pow7(glx::add_canon(x[0], k0)))), ap[t]);
                 }
             } break;
             case ZKGPU_GATE_CONDITIONAL_SWAP4:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(17 * t) * cw;
                     const uint64_t sw = x[8 * cw];
 #pragma unroll 1
@@ -168,9 +227,9 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
                 }
                 break;
             case ZKGPU_GATE_ZERO_CHECK_WITNESS: {
-                const uint64_t* pw = w + (size_t)p.NP * cw;   // plain witness columns start at column NP
+                const uint64_t* pw = w + (size_t)n_copy * cw;   // plain witness cells follow the copy columns in the tile
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(2 * t) * cw;
                     uint64_t xv = x[0], zf = x[cw];
                     dote_add(d, gl::sub(gl::mul(xv, pw[(size_t)t * cw]), gl::sub(1, zf)), ap[2 * t]);
@@ -179,7 +238,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             } break;
             case ZKGPU_GATE_DOT_PRODUCT4:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(9 * t) * cw;
                     uint64_t s = gl::add(gl::add(gl::mul(x[0], x[cw]), gl::mul(x[2 * cw], x[3 * cw])),
                                          gl::add(gl::mul(x[4 * cw], x[5 * cw]), gl::mul(x[6 * cw], x[7 * cw])));
@@ -188,7 +247,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
                 break;
             case ZKGPU_GATE_U8X4_FMA:
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(26 * t) * cw;
                     // sum_{i,j} a_i b_j 2^(8(i+j)), grouped by i+j; then the linear part, byte position by byte position
                     uint64_t a[4], b[4];
@@ -215,7 +274,7 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
             case ZKGPU_GATE_FMA_EXT: {
                 const gl::e2 k0 = gl::make2(gk[0], gk[cs]), k1 = gl::make2(gk[2 * cs], gk[3 * cs]);
 #pragma unroll 1
-                for (uint32_t t = 0; t < inst; t++) {
+                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(8 * t) * cw;
                     gl::e2 ab = gl::mul(gl::make2(x[0], x[cw]), gl::make2(x[2 * cw], x[3 * cw]));
                     gl::e2 r = gl::sub(gl::add(gl::mul(k0, ab), gl::mul(k1, gl::make2(x[4 * cw], x[5 * cw]))), gl::make2(x[6 * cw], x[7 * cw]));
@@ -228,8 +287,19 @@ __global__ void __launch_bounds__(128, 8) quotient_gates_kernel(const __grid_con
         const uint64_t sel = selector(kc, cs, gt.path_len, gt.path_bits);
         acc = gl::add(acc, gl::mul_base(dote_reduce(d), sel));
     }
-    p.t0[j] = acc.c0;
-    p.t1[j] = acc.c1;
+    red[(0 * QG_SPLIT + warp) * QG_P + lane] = acc.c0;
+    red[(1 * QG_SPLIT + warp) * QG_P + lane] = acc.c1;
+    __syncthreads();
+    if (warp == 0 && lane < npts) {
+        uint64_t r0 = red[lane], r1 = red[QG_SPLIT * QG_P + lane];
+#pragma unroll
+        for (int q = 1; q < QG_SPLIT; q++) {
+            r0 = gl::add(r0, red[q * QG_P + lane]);
+            r1 = gl::add(r1, red[(QG_SPLIT + q) * QG_P + lane]);
+        }
+        p.t0[j0 + lane] = r0;
+        p.t1[j0 + lane] = r1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ flattened Poseidon2 gate
@@ -376,7 +446,7 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
     for (uint32_t c = 0; c < p.C; c++) {
         gl::e2 num = gl::make2(1, 0), dn = gl::make2(1, 0);
         const uint32_t i1 = min((c + 1) * QD, p.NP);
-#pragma unroll 1
+        ZK_UNROLL(ZK_PERM_UNROLL)
         for (uint32_t i = c * QD; i < i1; i++) {
             const uint64_t wv = w[(size_t)i * cw];
             gl::e2 a = gl::add(bkx, p.gamma);
@@ -401,7 +471,15 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
 void launch_quotient_coset(Ctx* ctx, const QuotParams& p) {
     const size_t N = (size_t)1 << p.g.log_n;
     const unsigned grid = (unsigned)((N + 127) / 128);
-    quotient_gates_kernel<<<grid, 128, 0, ctx->stream>>>(p);
+    {
+        const size_t smem = quotient_gates_smem(p.g);
+        static size_t attr_smem[64] = {};   // per device: the opt-in limit only ever grows
+        if (smem > attr_smem[ctx->device & 63]) {
+            CUDA_CHECK(cudaFuncSetAttribute(quotient_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem[ctx->device & 63] = smem;
+        }
+        quotient_gates_kernel<<<(unsigned)((N + QG_P - 1) / QG_P), 32 * QG_SPLIT, smem, ctx->stream>>>(p);
+    }
     CUDA_CHECK(cudaGetLastError());
     ctx->kernel_launches++;
     if (p.p2_gate != 0xFFFFFFFFu) {

@@ -30,6 +30,10 @@ void orc_poseidon2_permute(uint64_t *s);
 void orc_merkle_build(const uint64_t *cols, size_t col_stride, size_t n_cols, size_t n_leaves, size_t elems_per_leaf, size_t cap_size,
                       uint64_t *tree_out);
 void orc_merkle_path(const uint64_t *tree, size_t n_leaves, size_t cap_size, size_t idx, uint64_t *path_out);
+int orc_merkle_verify(const uint64_t *leaf_els, size_t leaf_len, const uint64_t *path, size_t path_len, const uint64_t *cap, size_t idx);
+void orc_fri_fold_leaf(const uint64_t *c0, const uint64_t *c1, size_t n, int log_dom, uint64_t shift, size_t base_idx, const uint64_t ch[2],
+                       uint64_t out[2]);
+void orc_eval_ext_poly_at_base(const uint64_t *c0, const uint64_t *c1, size_t n, uint64_t x, uint64_t out[2]);
 void orc_fri_fold(const uint64_t *in_c0, const uint64_t *in_c1, int log_dom, uint64_t shift, const uint64_t ch[2], uint64_t *out_c0,
                   uint64_t *out_c1);
 
@@ -612,4 +616,245 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     free(mono_2); free(lde_2); free(tree_2); free(mono_q); free(lde_q); free(tree_q);
     tr_free(&tr);
     return written;
+}
+
+/* ------------------------------------------------------------------ verifier (the oracle's own acceptance check)
+ * Mirrors `verifier.verify::<H, TR, POW>((), vk, proof)` (/root/reference/src/prover_utils.rs:351-372) for the flat proof buffer.
+ * Written independently of the product's CPU verifier (csrc/host.cu): the DEEP check is deep_point() above -- the function the
+ * golden fixtures pin --, the FRI check is orc_fri_fold_leaf (pinned by tests/golden/fri_chain_*.json), and the quotient identity
+ * at z evaluates every gate over Ext2 WITHOUT an Ext2 gate library: a gate relation is a polynomial of degree <= 7 in its cells
+ * and constants, so R(a + u b) is recovered from the eight base-field evaluations R(a + t b), t = 0..7, of the base-field gate
+ * library (gates.h) by interpolation in t followed by t^2 -> 7.
+ * Returns 0 when the proof is accepted, otherwise a positive code; `msg` gets a one-line reason. */
+#define V_FAIL(code, ...) do { snprintf(msg, msg_len, __VA_ARGS__); rc = (code); goto done; } while (0)
+
+static void interp8_init(uint64_t minv[8][8]) { /* inverse of the Vandermonde matrix of the points 0..7 */
+    uint64_t a[8][16];
+    for (int i = 0; i < 8; i++) {
+        uint64_t pw = 1;
+        for (int j = 0; j < 8; j++) { a[i][j] = pw; pw = gl_mul(pw, (uint64_t)i); a[i][8 + j] = (i == j); }
+    }
+    for (int c = 0; c < 8; c++) {
+        int piv = c;
+        while (a[piv][c] == 0) piv++;
+        if (piv != c) for (int j = 0; j < 16; j++) { uint64_t t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+        uint64_t inv = gl_inv(a[c][c]);
+        for (int j = 0; j < 16; j++) a[c][j] = gl_mul(a[c][j], inv);
+        for (int r = 0; r < 8; r++) {
+            if (r == c || a[r][c] == 0) continue;
+            uint64_t f = a[r][c];
+            for (int j = 0; j < 16; j++) a[r][j] = gl_sub(a[r][j], gl_mul(f, a[c][j]));
+        }
+    }
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) minv[i][j] = a[i][8 + j];
+}
+
+EXPORT int orc_verify(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, const uint64_t *vk_cap, const uint64_t *proof, size_t len,
+                      char *msg, size_t msg_len) {
+    int rc = 0;
+    shape_t sh; make_shape(g, cfg, &sh);
+    const uint32_t W = sh.W, S = sh.S, S2 = sh.S2, Q = sh.Q, NP = n_perm(g), C = n_chunks(g), E2 = n_s2_ext(g), QD = g->quotient_degree;
+    const uint32_t n_at_z = sh.n_at_z, n_at_0 = sh.n_at_0, NF = cfg->n_fri_oracles;
+    const size_t N = sh.N, LN = sh.LN, cap = cfg->cap_size;
+    const int log_n = g->log_n, log_ln = log_n + cfg->log_lde;
+    const uint64_t omega = gl_omega(log_n);
+    open_src *src = NULL; gl2 *wz = NULL, *sz = NULL, *ez = NULL, *qz = NULL, *phip = NULL; uint64_t *scratch = NULL, *cells = NULL;
+    chal_t ch; memset(&ch, 0, sizeof(ch));
+    tr_t tr; tr_init(&tr);
+    if (msg_len) msg[0] = 0;
+    if (len != orc_proof_size_u64(g, cfg)) V_FAIL(1, "proof length does not match geometry and config");
+    if (proof[0] != PROOF_MAGIC || proof[1] != (uint64_t)log_n || proof[2] != cfg->log_lde || proof[3] != cap || proof[4] != cfg->n_queries ||
+        proof[5] != NF || proof[10] != n_at_z || proof[12] != n_at_0 || proof[13] != g->n_public_inputs || proof[14] != sh.n_final)
+        V_FAIL(2, "proof header does not match geometry and config");
+    for (uint32_t k = 0; k < NF; k++) if (proof[16 + k] != cfg->fri_schedule[k]) V_FAIL(2, "folding schedule in the header differs");
+    for (size_t i = 32; i < len; i++) if (proof[i] >= GL_P) V_FAIL(3, "non-canonical field element in the proof");
+
+    const uint64_t *p = proof + 32;
+    const uint64_t *pi = p; p += g->n_public_inputs;
+    const uint64_t *cap_w = p; p += cap * 4;
+    const uint64_t *cap_2 = p; p += cap * 4;
+    const uint64_t *cap_q = p; p += cap * 4;
+    const uint64_t *fin0 = p; p += sh.n_final;
+    const uint64_t *fin1 = p; p += sh.n_final;
+    const gl2 *at_z = (const gl2 *)p; p += 2 * n_at_z;
+    const gl2 at_zw = *(const gl2 *)p; p += 2;
+    const gl2 *at_0 = (const gl2 *)p; p += 2 * n_at_0;
+    const uint64_t *fri_cap[ZKGPU_MAX_FRI_ORACLES];
+    for (uint32_t k = 0; k < NF; k++) { fri_cap[k] = p; p += sh.fri_cap[k] * 4; }
+    const uint64_t *queries = p;
+
+    /* ---- Fiat-Shamir replay, in the prover's order */
+    tr_absorb(&tr, vk_cap, cap * 4);
+    tr_absorb(&tr, pi, g->n_public_inputs);
+    tr_absorb(&tr, cap_w, cap * 4);
+    ch.beta = tr_challenge_ext(&tr); ch.gamma = tr_challenge_ext(&tr);
+    if (g->lookup_reps) { ch.lbeta = tr_challenge_ext(&tr); ch.lgamma = tr_challenge_ext(&tr); }
+    tr_absorb(&tr, cap_2, cap * 4);
+    ch.alpha = tr_challenge_ext(&tr);
+    tr_absorb(&tr, cap_q, cap * 4);
+    const gl2 z = tr_challenge_ext(&tr);
+    tr_absorb(&tr, (const uint64_t *)at_z, 2 * n_at_z);
+    tr_absorb(&tr, (const uint64_t *)&at_zw, 2);
+    tr_absorb(&tr, (const uint64_t *)at_0, 2 * n_at_0);
+    const gl2 phi = tr_challenge_ext(&tr);
+    gl2 fri_ch[ZKGPU_MAX_FRI_ORACLES];
+    for (uint32_t k = 0; k < NF; k++) { tr_absorb(&tr, fri_cap[k], sh.fri_cap[k] * 4); fri_ch[k] = tr_challenge_ext(&tr); }
+    tr_absorb(&tr, fin0, sh.n_final);
+    tr_absorb(&tr, fin1, sh.n_final);
+
+    /* ---- openings back in oracle order */
+    src = (open_src *)malloc(sizeof(open_src) * n_at_z);
+    if (opening_sources(g, src) != n_at_z) V_FAIL(4, "opening count mismatch");
+    wz = (gl2 *)calloc(W, sizeof(gl2)); sz = (gl2 *)calloc(S, sizeof(gl2)); ez = (gl2 *)calloc(E2, sizeof(gl2)); qz = (gl2 *)calloc(QD, sizeof(gl2));
+    for (uint32_t i = 0; i < n_at_z; i++) {
+        gl2 *dst = src[i].kind == 0 ? wz : src[i].kind == 1 ? sz : src[i].kind == 2 ? ez : qz;
+        dst[src[i].idx] = at_z[i];
+    }
+    const gl2 *sigma = sz, *consts = sz + NP, *tables = sz + NP + g->n_const_cols;
+
+    /* ---- quotient identity at z */
+    {
+        const uint32_t n_terms = count_terms(g);
+        gl2 *ap = (gl2 *)malloc(sizeof(gl2) * n_terms);
+        ap[0] = gl2_make(1, 0);
+        for (uint32_t i = 1; i < n_terms; i++) ap[i] = gl2_mul(ap[i - 1], ch.alpha);
+        ch.alpha_pow = ap;
+        uint64_t minv[8][8]; interp8_init(minv);
+        const uint32_t n_cells = g->n_copy + g->n_witness_plain;
+        scratch = alloc_u64(8 * 1024); cells = alloc_u64((size_t)8 * (n_cells + 64));
+        gl2 acc = gl2_make(0, 0);
+        uint32_t k = 0;
+        for (uint32_t gi = 0; gi < g->n_gates; gi++) {
+            const zkgpu_gate *gt = &g->gates[gi];
+            uint32_t nrel = 0;
+            for (uint64_t t = 0; t < 8; t++) { /* R(a + t b): cells and gate constants moved along the same line */
+                uint64_t *cv = cells + t * (n_cells + 64), *kv = cv + n_cells;
+                for (uint32_t c = 0; c < n_cells; c++) {
+                    const gl2 v = wz[c < g->n_copy ? c : NP + (c - g->n_copy)];
+                    cv[c] = gl_add(v.c0, gl_mul(t, v.c1));
+                }
+                for (uint32_t c = 0; c + gt->path_len < g->n_const_cols && c < 64; c++) {
+                    const gl2 v = consts[gt->path_len + c];
+                    kv[c] = gl_add(v.c0, gl_mul(t, v.c1));
+                }
+                nrel = og_eval_gate(gt, g, cv, kv, ORC_P2_RC, scratch + t * 1024);
+            }
+            if (!nrel) continue;
+            gl2 sel = gl2_make(1, 0);
+            for (uint32_t b = 0; b < gt->path_len; b++)
+                sel = gl2_mul(sel, ((gt->path_bits >> b) & 1) ? consts[b] : gl2_sub(gl2_make(1, 0), consts[b]));
+            gl2 ga = gl2_make(0, 0);
+            for (uint32_t r = 0; r < nrel; r++) {
+                gl2 val = gl2_make(0, 0);
+                uint64_t p7 = 1; /* 7^(d/2) */
+                for (int d = 0; d < 8; d++) {
+                    uint64_t coef = 0;
+                    for (int t = 0; t < 8; t++) coef = gl_add(coef, gl_mul(minv[d][t], scratch[t * 1024 + r]));
+                    if (d & 1) { val.c1 = gl_add(val.c1, gl_mul(coef, p7)); p7 = gl_mul(p7, 7); }
+                    else val.c0 = gl_add(val.c0, gl_mul(coef, p7));
+                }
+                ga = gl2_add(ga, gl2_mul(ap[k + r], val));
+            }
+            acc = gl2_add(acc, gl2_mul(ga, sel));
+            k += nrel;
+        }
+        if (g->has_boolean_col) {
+            const gl2 b = wz[g->n_copy];
+            acc = gl2_add(acc, gl2_mul(ap[k++], gl2_sub(gl2_sqr(b), b)));
+        }
+        if (g->lookup_reps) {
+            const uint32_t LW = g->lookup_width;
+            const gl2 *lw = wz + g->n_copy + (g->has_boolean_col ? 1 : 0);
+            gl2 gp[16]; gp[0] = gl2_make(1, 0);
+            for (uint32_t j = 1; j <= LW; j++) gp[j] = gl2_mul(gp[j - 1], ch.lgamma);
+            const gl2 tid = gl2_mul(gp[LW], consts[g->table_id_col]);
+            for (uint32_t i = 0; i < g->lookup_reps; i++) {
+                gl2 den = gl2_add(ch.lbeta, tid);
+                for (uint32_t j = 0; j < LW; j++) den = gl2_add(den, gl2_mul(gp[j], lw[i * LW + j]));
+                acc = gl2_add(acc, gl2_mul(ap[k++], gl2_sub(gl2_mul(ez[C + i], den), gl2_make(1, 0))));
+            }
+            gl2 den = ch.lbeta;
+            for (uint32_t j = 0; j <= LW; j++) den = gl2_add(den, gl2_mul(gp[j], tables[j]));
+            acc = gl2_add(acc, gl2_mul(ap[k++], gl2_sub(gl2_mul(ez[C + g->lookup_reps], den), wz[W - 1])));
+        }
+        const gl2 zn_minus_1 = gl2_sub(gl2_pow(z, N), gl2_make(1, 0));
+        {
+            const gl2 l0 = gl2_mul(zn_minus_1, gl2_inv(gl2_mul_base(gl2_sub(z, gl2_make(1, 0)), (uint64_t)N % GL_P)));
+            acc = gl2_add(acc, gl2_mul(ap[k++], gl2_mul(gl2_sub(ez[0], gl2_make(1, 0)), l0)));
+            gl2 kx = z;
+            for (uint32_t j = 0; j < C; j++) {
+                gl2 num = gl2_make(1, 0), den = gl2_make(1, 0);
+                for (uint32_t i = j * QD; i < (j + 1) * QD && i < NP; i++) {
+                    num = gl2_mul(num, gl2_add(gl2_add(gl2_mul(ch.beta, kx), ch.gamma), wz[i]));
+                    den = gl2_mul(den, gl2_add(gl2_add(gl2_mul(ch.beta, sigma[i]), ch.gamma), wz[i]));
+                    kx = gl2_mul_base(kx, GL_GEN);
+                }
+                const gl2 cur = (j + 1 < C) ? ez[j + 1] : at_zw;
+                acc = gl2_add(acc, gl2_mul(ap[k++], gl2_sub(gl2_mul(cur, den), gl2_mul(ez[j], num))));
+            }
+        }
+        if (k != n_terms) V_FAIL(5, "term count mismatch");
+        gl2 quot = gl2_make(0, 0);
+        const gl2 zn = gl2_pow(z, N);
+        for (uint32_t c = QD; c-- > 0;) quot = gl2_add(gl2_mul(quot, zn), qz[c]);
+        if (!gl2_eq(acc, gl2_mul(quot, zn_minus_1))) V_FAIL(6, "quotient identity fails at z");
+    }
+    /* ---- lookup: sum_i A_i(0) = B(0) */
+    if (n_at_0) {
+        gl2 s = gl2_make(0, 0);
+        for (uint32_t i = 0; i + 1 < n_at_0; i++) s = gl2_add(s, at_0[i]);
+        if (!gl2_eq(s, at_0[n_at_0 - 1])) V_FAIL(7, "lookup sum check fails at 0");
+    }
+    /* ---- queries */
+    {
+        const uint32_t n_deep = n_at_z + 1 + n_at_0 + g->n_public_inputs;
+        phip = (gl2 *)malloc(sizeof(gl2) * n_deep);
+        phip[0] = gl2_make(1, 0);
+        for (uint32_t i = 1; i < n_deep; i++) phip[i] = gl2_mul(phip[i - 1], phi);
+        gl2 sum_at_z = gl2_make(0, 0);
+        for (uint32_t i = 0; i < n_at_z; i++) sum_at_z = gl2_add(sum_at_z, gl2_mul(phip[i], at_z[i]));
+        uint64_t pi_root[ZKGPU_MAX_PUBLIC_INPUTS];
+        for (uint32_t i = 0; i < g->n_public_inputs; i++) pi_root[i] = gl_pow(omega, g->pi_row[i]);
+        const gl2 zw = gl2_mul_base(z, omega);
+        const uint64_t omega_ln = gl_omega(log_ln);
+        const uint64_t *qp = queries;
+        for (uint32_t q = 0; q < cfg->n_queries; q++) {
+            const size_t idx = (size_t)(tr_challenge(&tr) & (uint64_t)(LN - 1));
+            const uint64_t *leaf[4], *caps[4] = {cap_w, cap_2, cap_q, vk_cap};
+            const uint32_t widths[4] = {W, S2, Q, S};
+            static const char *names[4] = {"witness", "stage 2", "quotient", "setup"};
+            for (int o = 0; o < 4; o++) {
+                leaf[o] = qp; qp += widths[o];
+                if (!orc_merkle_verify(leaf[o], widths[o], qp, sh.depth, caps[o], idx)) V_FAIL(8, "query %u: %s oracle Merkle path fails", q, names[o]);
+                qp += sh.depth * 4;
+            }
+            const uint64_t x = gl_mul(GL_GEN, gl_pow(omega_ln, bitrev32((uint32_t)idx, log_ln)));
+            gl2 expect = deep_point(g, src, n_at_z, n_at_0, leaf[0], leaf[3], leaf[1], leaf[2], phip, sum_at_z, at_zw, at_0, pi, pi_root, x, z, zw);
+            size_t di = idx;
+            uint64_t shift = GL_GEN;
+            for (uint32_t k = 0; k < NF; k++) {
+                const uint32_t s = cfg->fri_schedule[k];
+                const size_t epl = (size_t)1 << s, lf = di >> s, pos = di & (epl - 1);
+                const uint64_t *c0 = qp, *c1 = qp + epl;
+                if (!orc_merkle_verify(qp, 2 * epl, qp + 2 * epl, sh.fri_depth[k], fri_cap[k], lf)) V_FAIL(9, "query %u: FRI oracle %u Merkle path fails", q, k);
+                if (c0[pos] != expect.c0 || c1[pos] != expect.c1)
+                    V_FAIL(10, k == 0 ? "query %u: DEEP value differs from FRI base oracle (oracle %u)" : "query %u: fold does not land in FRI oracle %u", q, k);
+                uint64_t cc[2] = {fri_ch[k].c0, fri_ch[k].c1}, out[2];
+                orc_fri_fold_leaf(c0, c1, epl, (int)sh.fri_dom_log[k], shift, lf << s, cc, out);
+                expect = gl2_make(out[0], out[1]);
+                for (uint32_t i = 0; i < s; i++) shift = gl_sqr(shift);
+                qp += 2 * epl + sh.fri_depth[k] * 4;
+                di = lf;
+            }
+            const int ldf = (int)sh.fri_dom_log[NF];
+            uint64_t out[2];
+            orc_eval_ext_poly_at_base(fin0, fin1, sh.n_final, gl_mul(shift, gl_pow(gl_omega(ldf), bitrev32((uint32_t)di, ldf))), out);
+            if (out[0] != expect.c0 || out[1] != expect.c1) V_FAIL(11, "query %u: last fold differs from the final polynomial", q);
+        }
+        if (*qp != 0) V_FAIL(12, "non-zero proof-of-work nonce (NoPow)");
+    }
+done:
+    free(src); free(wz); free(sz); free(ez); free(qz); free(phip); free(scratch); free(cells); free(ch.alpha_pow);
+    tr_free(&tr);
+    return rc;
 }

@@ -52,6 +52,7 @@ class Oracle:
         for nm in ("orc_num_witness_cols", "orc_num_setup_cols", "orc_num_stage2_cols"):
             getattr(L, nm).restype = ctypes.c_uint32; getattr(L, nm).argtypes = [vp]
         L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
+        L.orc_verify.restype = ci; L.orc_verify.argtypes = [vp, vp, vp, vp, sz, ctypes.c_char_p, sz]
         L.orc_set_threads.restype = ci; L.orc_set_threads.argtypes = [ci]
         L.orc_synth_trace.restype = ci; L.orc_synth_trace.argtypes = [vp, c_u64, c_u64, ci, vp, vp]
 
@@ -165,6 +166,13 @@ class Oracle:
         w = self.lib.orc_prove(ctypes.byref(geo), ctypes.byref(cfg), self._p(wit_cols), self._p(setup_cols), self._p(proof), n)
         assert w == n, (w, n)
         return proof
+
+    def verify(self, geo, cfg, vk_cap, proof):
+        """The oracle's own verifier (oracle/prover.c orc_verify), independent of the product's zkgpu_verify: (ok, message)."""
+        cap = np.ascontiguousarray(vk_cap, dtype=np.uint64); pr = np.ascontiguousarray(proof, dtype=np.uint64)
+        buf = ctypes.create_string_buffer(256)
+        rc = self.lib.orc_verify(ctypes.byref(geo), ctypes.byref(cfg), self._p(cap), self._p(pr), pr.size, buf, 256)
+        return rc == 0, buf.value.decode()
 
     def set_threads(self, n):
         return int(self.lib.orc_set_threads(int(n)))

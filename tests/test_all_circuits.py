@@ -23,7 +23,10 @@ def test_oracle_proves_and_verifies_every_circuit(oracle, key, geo):
     cfg = G.make_proof_config(8, 2, 16, security_level=6)
     wit, setup = PU.synth_trace(g, seed=5)
     proof = oracle.prove(g, cfg, wit, setup)
-    ok, msg = PU.verify_proof(g, cfg, oracle.setup_cap(g, cfg, setup), proof)
+    cap = oracle.setup_cap(g, cfg, setup)
+    ok, msg = PU.verify_proof(g, cfg, cap, proof)
+    assert ok, msg
+    ok, msg = oracle.verify(g, cfg, cap, proof)   # two independent acceptance checks: product verifier and oracle verifier
     assert ok, msg
 
 
@@ -41,6 +44,8 @@ def test_gpu_proof_of_every_circuit_is_bit_identical_to_oracle(gpu, oracle, key,
     diff = np.nonzero(proof != ref)[0]
     assert diff.size == 0, f"first differing u64 at {int(diff[0])}"
     ok, msg = PU.verify_proof(g, cfg, sd.vk_cap, proof)
+    assert ok, msg
+    ok, msg = oracle.verify(g, cfg, sd.vk_cap, proof)
     assert ok, msg
     sd.close()
 
@@ -60,6 +65,8 @@ def test_oracle_proves_and_verifies_compression_circuits(oracle, key, geo, cfg):
     cap = oracle.setup_cap(g, c, setup)
     ok, msg = PU.verify_proof(g, c, cap, proof)
     assert ok, msg
+    ok, msg = oracle.verify(g, c, cap, proof)
+    assert ok, msg
     # a plain witness cell is covered by the gate relations: corrupting one breaks the quotient identity
     if g.n_witness_plain:
         wit2 = wit.copy()
@@ -70,6 +77,8 @@ def test_oracle_proves_and_verifies_compression_circuits(oracle, key, geo, cfg):
         bad = oracle.prove(g, c, wit2, setup)
         ok2, msg2 = PU.verify_proof(g, c, cap, bad)
         assert not ok2 and "quotient" in msg2
+        ok3, msg3 = oracle.verify(g, c, cap, bad)
+        assert not ok3 and "quotient" in msg3
 
 
 @pytest.mark.gpu

@@ -31,10 +31,12 @@ def test_shapes_match_reference_tables():
     assert cols == dict(witness=156, permuted=155, setup=167, stage2=58, quotient=16)
 
 
-def test_oracle_proof_verifies(small):
+def test_oracle_proof_verifies(oracle, small):
     geo, cfg, wit, setup, vk_cap, proof = small
     assert proof.size == PU.proof_size_u64(geo, cfg)
     ok, msg = PU.verify_proof(geo, cfg, vk_cap, proof)
+    assert ok, msg
+    ok, msg = oracle.verify(geo, cfg, vk_cap, proof)     # the oracle's own, independently written verifier
     assert ok, msg
 
 
@@ -53,10 +55,12 @@ def test_unsatisfied_witness_is_rejected(oracle, small, capfd):
     proof = oracle.prove(geo, cfg, bad, setup)
     ok, msg = PU.verify_proof(geo, cfg, vk_cap, proof)
     assert not ok
+    ok, msg = oracle.verify(geo, cfg, vk_cap, proof)
+    assert not ok and "quotient" in msg
 
 
 @pytest.mark.parametrize("what", ["public_input", "witness_cap", "values_at_z", "fri_leaf", "final_monomial", "vk_cap", "query_leaf"])
-def test_corrupted_proof_is_rejected(small, what):
+def test_corrupted_proof_is_rejected(oracle, small, what):
     geo, cfg, wit, setup, vk_cap, proof = small
     p = proof.copy()
     cap = vk_cap.copy()
@@ -87,6 +91,8 @@ def test_corrupted_proof_is_rejected(small, what):
         p[off_q + 3] ^= np.uint64(1)
     ok, msg = PU.verify_proof(geo, cfg, cap, p)
     assert not ok and msg
+    ok2, msg2 = oracle.verify(geo, cfg, cap, p)          # both verifiers reject every corruption of wrapper_negative_tests.rs:112-206
+    assert not ok2 and msg2
 
 
 PU_P = (1 << 64) - (1 << 32) + 1
