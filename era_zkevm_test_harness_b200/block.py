@@ -122,6 +122,28 @@ def plan_block(base_instances: Dict[int, int], base_keys: Dict[int, str], leaf_k
     return plan
 
 
+SYNTHETIC_NOTE = {
+    "synthetic": True,
+    "why": "Artefacts of this directory are NOT interchangeable with the reference's files of the same names: (1) the Poseidon2 "
+           "parameters of the un-vendored boojum crate are unpinned (DESIGN.md section 5), so caps, challenges and query indexes "
+           "differ from boojum's; (2) witnesses and setup columns are synthetic satisfying traces of each circuit's geometry, and "
+           "recursion / compression jobs do not verify their children in-circuit (the recursive-verifier synthesis is host Rust).",
+}
+
+
+def synthetic_root(out_dir):
+    """Everything this package writes in the reference's file layout goes under <out_dir>/synthetic/, next to a manifest saying
+    why it must not be mistaken for reference-compatible proofs or verification keys."""
+    root = os.path.join(out_dir, "synthetic")
+    os.makedirs(root, exist_ok=True)
+    manifest = os.path.join(root, "SYNTHETIC.json")
+    if not os.path.exists(manifest):
+        import json
+        with open(manifest, "w") as f:
+            json.dump(SYNTHETIC_NOTE, f, indent=2)
+    return root
+
+
 def seed_for(job: Job, proofs: Dict[str, np.ndarray], block_seed: int) -> int:
     """Seed of a job's synthetic trace: the block seed and the job identity for base jobs, a digest of the flat child proofs
     for aggregation jobs (so the data dependency between stages is real)."""
@@ -188,15 +210,24 @@ def prove_block(plan: BlockPlan, prove: Callable[[Job, int], np.ndarray], block_
         for i in mine:
             local[i] = np.ascontiguousarray(prove(jobs[i], seeds[i]), dtype=np.uint64)
         gathered = gather_stage(local, len(jobs), device=device, group=group)
+        failed = ""
         if rank == 0:
             for j, p in zip(jobs, gathered):
                 if verify is not None and not verify(j, p):
-                    raise RuntimeError(f"block: proof {j.file} does not verify")
+                    failed = j.file
+                    break
                 proofs[j.file] = p
                 if out_dir is not None:
-                    path = os.path.join(out_dir, j.file)
+                    path = os.path.join(synthetic_root(out_dir), j.file)
                     os.makedirs(os.path.dirname(path), exist_ok=True)
                     proof_format.save_proof_json(path, p, j.variant, security_level=security_level)
+        if multi:   # every rank learns about a failed verification before anyone raises: nobody is left in the next collective
+            flag = torch.tensor([1 if failed else 0], dtype=torch.int64, device=device if device is not None else "cpu")
+            dist.broadcast(flag, src=0, group=group)
+            if int(flag.item()):
+                raise RuntimeError(f"block: a proof of stage {name} does not verify" + (f" ({failed})" if failed else ""))
+        elif failed:
+            raise RuntimeError(f"block: proof {failed} does not verify")
         report.append({"stage": name, "jobs": len(jobs), "seconds": time.time() - t0})
     return {"proofs": proofs if rank == 0 else None, "stages": report}
 
@@ -214,7 +245,10 @@ class GpuBlockProver:
         self.vk_caps: Dict[str, np.ndarray] = {}
         self.seconds = {"synth_trace": 0.0, "setup": 0.0, "prove": 0.0}
         self.pool = ThreadPoolExecutor(max_workers=host_threads) if host_threads > 1 else None
-        self.pending = {}   # (geometry key, witness seed) -> future of the witness columns
+        # witness generation takes a pinned buffer each: two generator threads keep one buffer free for the proof in flight
+        self.gen_pool = ThreadPoolExecutor(max_workers=2) if host_threads > 1 else None
+        self.pinned, self.staged, self.order, self.next_slot = None, {}, [], 0
+        self.pending = {}   # (geometry key, witness seed) -> future of (pinned buffer, witness columns)
         self.pending_setup = {}   # geometry key -> future of the setup columns
         self.prove_ms = {}        # file -> wall ms of the prove call alone (host witness in, proof out)
 
@@ -248,8 +282,25 @@ class GpuBlockProver:
         self.vk_caps[key] = sd.vk_cap.copy()
         return sd
 
+    def _pinned(self):
+        if self.pinned is None:   # three buffers of the widest witness: one being proven, one staged, one being generated
+            words = max(g.n_witness << g.log_n for g, _ in self.circuits.values())
+            self.pinned = PU.PinnedPool(3, words)
+        return self.pinned
+
+    def _generate(self, geo, seed):
+        buf = self._pinned().take()
+        try:
+            wit, _ = PU.synth_trace(geo, seed=self.setup_seed, witness_seed=seed, out_witness=buf)
+        except Exception:
+            self.pinned.give(buf)
+            raise
+        return buf, wit
+
     def prefetch(self, jobs_and_seeds):
-        """starts generating the witnesses of the given jobs on host threads (zkgpu_synth_trace_instance releases the GIL)"""
+        """starts generating the witnesses of the given jobs, in proving order, on host threads into pinned buffers
+        (zkgpu_synth_trace_instance releases the GIL); the order is also the look-ahead order of `prove`"""
+        self.order = [(job.geometry_key, seed) for job, seed in jobs_and_seeds]
         if self.pool is None:
             return
         for job, seed in jobs_and_seeds:
@@ -257,31 +308,59 @@ class GpuBlockProver:
             if job.geometry_key not in self.resident and job.geometry_key not in self.pending_setup:
                 self.pending_setup[job.geometry_key] = self.pool.submit(
                     lambda g=geo: PU.synth_trace(g, seed=self.setup_seed, witness_seed=self.setup_seed)[1])
-            self.pending[(job.geometry_key, seed)] = self.pool.submit(
-                lambda g=geo, sd=seed: PU.synth_trace(g, seed=self.setup_seed, witness_seed=sd)[0])
+            self.pending[(job.geometry_key, seed)] = self.gen_pool.submit(self._generate, geo, seed)
+
+    def _stage(self, key, seed, slot, wait):
+        """uploads the witness of (key, seed) into a staging slot if its generation is finished (or `wait`); -> staged entry"""
+        fut = self.pending.get((key, seed))
+        if fut is None or not (wait or fut.done()) or key not in self.resident:
+            return None
+        t0 = time.time()
+        buf, wit = fut.result()
+        self.seconds["synth_trace"] += time.time() - t0   # only the time the GPU actually waited
+        del self.pending[(key, seed)]
+        PU.stage_witness(self.ctx, self.resident[key], wit, slot)
+        self.staged[(key, seed)] = (slot, buf)
+        return self.staged[(key, seed)]
 
     def prove(self, job: Job, seed: int) -> np.ndarray:
-        sd = self.setup(job.geometry_key)
-        fut = self.pending.pop((job.geometry_key, seed), None)
-        if fut is not None:
-            t0 = time.time()
-            wit = fut.result()
-            self.seconds["synth_trace"] += time.time() - t0   # only the time the GPU actually waited
-        else:
-            wit, _ = self._trace(job.geometry_key, seed)
+        """Pinned witness -> zkgpu_witness_stage -> zkgpu_prove_staged; the NEXT job's witness (prefetch order) is staged into the
+        other slot before this proof starts, so its upload runs under this proof (the bench's staged mode, bench.py)."""
+        key = job.geometry_key
+        sd = self.setup(key)
+        me = (key, seed)
+        if me not in self.staged:
+            if me not in self.pending:     # not prefetched: generate now, on this thread
+                from concurrent.futures import Future
+                self.pending[me] = Future()
+                self.pending[me].set_result(self._generate(self.circuits[key][0], seed))
+            self._stage(key, seed, self.next_slot, wait=True)
+            self.next_slot ^= 1
+        slot, buf = self.staged.pop(me)
+        if me in self.order:               # look ahead: stage the following job if its witness and setup are ready
+            i = self.order.index(me)
+            if i + 1 < len(self.order) and self.order[i + 1] not in self.staged:
+                if self._stage(*self.order[i + 1], slot ^ 1, wait=False) is not None:
+                    self.next_slot = slot
         t0 = time.time()
-        proof = PU.prove_circuit(self.ctx, sd, wit)
+        proof = PU.prove_staged(self.ctx, sd, slot)
         dt = time.time() - t0
+        self.pinned.give(buf)
         self.seconds["prove"] += dt
         self.prove_ms[job.file] = round(1e3 * dt, 1)
         return proof
 
     def close(self):
+        if self.gen_pool is not None:
+            self.gen_pool.shutdown(wait=True, cancel_futures=True)
         if self.pool is not None:
             self.pool.shutdown(wait=True, cancel_futures=True)
         for sd in self.resident.values():
             sd.close()
         self.resident.clear()
+        if self.pinned is not None:
+            self.pinned.close()
+            self.pinned = None
 
 
 def circuit_table(fixture, log_n=None, compression_log_n=None):

@@ -3,6 +3,9 @@
   generate_circuit_setup_data   <-> compute_setups.rs:316-401  (one circuit type -> CircuitSetupData)
   generate_base_layer_vks       <-> compute_setups.rs:412-436  (loop over all basic circuits, store the VKs)
   generate_recursive_layer_vks  <-> compute_setups.rs:439-586  (leaf types, node, scheduler)
+  generate_recursive_layer_vks_and_proofs <-> the same function's self-check: every leaf and the node circuit is PROVEN once with a
+                                    placeholder witness right after its setup and the proof verified against the fresh VK
+                                    (compute_setups.rs:479-496, :521-538), so a setup that cannot prove never reaches disk
 
 and of the file names the reference's `LocalFileDataSource` uses for them
 (src/data_source/local_file_data_source.rs:59-64, :95-113, :237-296): `{root}/base_layer/vk_{type}.json`,
@@ -51,6 +54,11 @@ def generate_circuit_setup_data(ctx, key, geo, entry, cfg=None, trace_source=_de
     return CircuitSetupData(key, entry["variant"], fp, sd)
 
 
+def _synthetic_root(root):
+    from .block import synthetic_root
+    return synthetic_root(root)
+
+
 def _write(path, obj):
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
@@ -65,7 +73,7 @@ def generate_base_layer_vks(ctx, root, fixture, log_n=None, trace_source=_defaul
         if log_n is not None and log_n != geo.log_n:
             geo = geo.scaled(log_n)
         data = generate_circuit_setup_data(ctx, f"base_{t}", geo, entry, trace_source=trace_source)
-        path = os.path.join(root, "base_layer", f"vk_{t}.json")
+        path = os.path.join(_synthetic_root(root), "base_layer", f"vk_{t}.json")
         _write(path, data.vk)
         data.setup.close()
         out[int(t)] = path
@@ -80,8 +88,44 @@ def generate_recursive_layer_vks(ctx, root, fixture, log_n=None, trace_source=_d
         if log_n is not None and log_n != geo.log_n:
             geo = geo.scaled(log_n)
         data = generate_circuit_setup_data(ctx, f"recursion_{key}", geo, entry, trace_source=trace_source)
-        path = os.path.join(root, "recursion_layer", names[key])
+        path = os.path.join(_synthetic_root(root), "recursion_layer", names[key])
         _write(path, data.vk)
         data.setup.close()
         out[key] = path
+    return out
+
+
+def generate_recursive_layer_vks_and_proofs(ctx, root, fixture, log_n=None, trace_source=_default_trace_source, witness_source=None):
+    """compute_setups.rs:439-586: set up every recursion-layer circuit type, prove it once with a placeholder witness, verify the
+    proof against the VK just computed, then store VK (and proof).  The reference's placeholder is the circuit synthesised over
+    default (empty-queue) inputs; here it is a synthetic satisfying trace of the circuit's geometry (`witness_source(geo)`).
+    -> {key: {"vk": path, "proof": path, "prove_seconds": s}}; raises if a proof does not verify (the reference asserts)."""
+    import time
+    from . import proof_format
+    names = {"scheduler": ("vk_1.json", "scheduler_proof.json", "SchedulerCircuit"),
+             "leaf_3": ("vk_3.json", "leaf_layer_proof_3_placeholder.json", "LeafLayerCircuit"),
+             "node": ("vk_node.json", "node_layer_proof_placeholder.json", "NodeLayerCircuit")}
+    if witness_source is None:
+        witness_source = lambda geo: PU.synth_trace(geo, seed=0x5E7)[0]   # noqa: E731  (the witness that goes with the default setup)
+    out = {}
+    for key, entry in fixture["recursion"].items():
+        geo = G.geometry_from_vk(entry, G.RECURSION_GATE_ORDER)
+        if log_n is not None and log_n != geo.log_n:
+            geo = geo.scaled(log_n)
+        cfg = G.recursion_layer_proof_config(geo.log_n) if hasattr(G, "recursion_layer_proof_config") else G.base_layer_proof_config(geo.log_n)
+        data = generate_circuit_setup_data(ctx, f"recursion_{key}", geo, entry, cfg=cfg, trace_source=trace_source)
+        t0 = time.time()
+        proof = PU.prove_circuit(ctx, data.setup, witness_source(geo))
+        dt = time.time() - t0
+        ok, msg = PU.verify_proof(geo, cfg, data.setup.vk_cap, proof)
+        if not ok:
+            data.setup.close()
+            raise RuntimeError(f"compute_setups: the placeholder proof of {key} does not verify against its fresh VK: {msg}")
+        vk_name, proof_name, variant = names[key]
+        vk_path = os.path.join(_synthetic_root(root), "recursion_layer", vk_name)
+        proof_path = os.path.join(_synthetic_root(root), "recursion_layer", proof_name)
+        _write(vk_path, data.vk)
+        proof_format.save_proof_json(proof_path, proof, variant)
+        data.setup.close()
+        out[key] = {"vk": vk_path, "proof": proof_path, "prove_seconds": dt}
     return out

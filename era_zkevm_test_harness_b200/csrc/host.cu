@@ -68,6 +68,7 @@ void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
     for (uint32_t i = 0; i < g.n_public_inputs; i++)
         ZK_REQUIRE(g.pi_col[i] < g.n_copy && g.pi_row[i] < ((uint32_t)1 << g.log_n), "geometry: public input location out of range");
     ZK_REQUIRE(cfg.log_lde >= 1 && cfg.log_lde <= 12, "config: log_lde out of range [1,12]");
+    ZK_REQUIRE(g.log_n + cfg.log_lde <= 32, "config: LDE domain larger than 2^32 (query indexes and bit reversals are 32-bit)");
     ZK_REQUIRE(cfg.cap_size >= 1 && (cfg.cap_size & (cfg.cap_size - 1)) == 0, "config: cap_size must be a power of two");
     ZK_REQUIRE(cfg.cap_size <= ((size_t)1 << (g.log_n + cfg.log_lde)), "config: cap larger than the LDE domain");
     ZK_REQUIRE(cfg.n_queries >= 1 && cfg.n_queries <= 1024, "config: n_queries out of range");

@@ -97,6 +97,8 @@ struct Setup {
     uint32_t E;            // cosets kept per column
     DevBuf vals, mono, cosets, tree;
     DevBuf var_maps;       // optional: [NP][N] u32 variable index per copy-permutation cell (zkgpu_setup_set_variable_maps)
+    DevBuf wit_maps;       // optional: [n_witness_plain][N] u32 witness index per plain witness cell (zkgpu_setup_set_witness_maps)
+    int64_t max_var_index = -1, max_wit_index = -1;   // largest non-placeholder entry of each map
     std::vector<uint64_t> vk_cap;
     int device;
 };
@@ -110,7 +112,7 @@ __global__ void materialize_columns_kernel(const uint32_t* __restrict__ maps, co
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cells) return;
     const uint32_t v = maps[i];
-    cols[i] = (v == ZKGPU_VAR_PLACEHOLDER || v >= n_vars) ? 0 : values[v];
+    cols[i] = v == ZKGPU_VAR_PLACEHOLDER ? 0 : values[v];   // v < n_vars is checked on the host against the map's largest index
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
@@ -992,15 +994,88 @@ int zkgpu_prove_staged(zkgpu_ctx* ctx, const zkgpu_setup* s, int slot, uint64_t*
     }
 }
 
+static int64_t upload_index_map(zk::Ctx& c, zk::DevBuf& dst, const uint32_t* h_maps, size_t cells) {
+    dst.alloc((cells + 1) / 2, c.stream);   // u32 cells in a u64 buffer
+    CUDA_CHECK(cudaMemcpyAsync(dst.p, h_maps, cells * 4, cudaMemcpyHostToDevice, c.stream));
+    int64_t mx = -1;
+    for (size_t i = 0; i < cells; i++)
+        if (h_maps[i] != ZKGPU_VAR_PLACEHOLDER && (int64_t)h_maps[i] > mx) mx = h_maps[i];
+    CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return mx;
+}
+
 int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_var_maps) {
     try {
         ZK_REQUIRE(ctx && s && s->s && h_var_maps, "set_variable_maps: NULL argument");
         CUDA_CHECK(cudaSetDevice(ctx->c.device));
         zk::Setup& st = *s->s;
-        const size_t cells = (size_t)st.sh.NP * st.sh.N;
-        st.var_maps.alloc((cells + 1) / 2, ctx->c.stream);   // u32 cells in a u64 buffer
-        CUDA_CHECK(cudaMemcpyAsync(st.var_maps.p, h_var_maps, cells * 4, cudaMemcpyHostToDevice, ctx->c.stream));
-        CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+        st.max_var_index = upload_index_map(ctx->c, st.var_maps, h_var_maps, (size_t)st.sh.NP * st.sh.N);
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
+}
+
+int zkgpu_setup_set_witness_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_wit_maps) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_wit_maps, "set_witness_maps: NULL argument");
+        CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        zk::Setup& st = *s->s;
+        ZK_REQUIRE(st.g.n_witness_plain > 0, "set_witness_maps: the circuit has no plain witness columns");
+        st.max_wit_index = upload_index_map(ctx->c, st.wit_maps, h_wit_maps, (size_t)st.g.n_witness_plain * st.sh.N);
+        return 0;
+    } catch (const zk::Error& e) {
+        zk::g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception& e) {
+        zk::g_last_error = e.what();
+        return 99;
+    }
+}
+
+int zkgpu_prove_from_hints(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
+                           const uint64_t* h_witness_values, size_t n_wits, const uint64_t* h_multiplicities, uint64_t* h_proof_out,
+                           size_t proof_capacity_u64) {
+    try {
+        ZK_REQUIRE(ctx && s && s->s && h_variable_values && h_proof_out, "prove_from_hints: NULL argument");
+        CUDA_CHECK(cudaSetDevice(ctx->c.device));
+        const zk::Setup& st = *s->s;
+        ZK_REQUIRE(st.var_maps.p != nullptr, "prove_from_hints: call zkgpu_setup_set_variable_maps first");
+        ZK_REQUIRE(n_vars < ZKGPU_VAR_PLACEHOLDER && n_wits < ZKGPU_VAR_PLACEHOLDER, "prove_from_hints: too many values");
+        ZK_REQUIRE(st.max_var_index < (int64_t)n_vars, "prove_from_hints: the variable maps reference an index >= n_vars");
+        ZK_REQUIRE(st.g.lookup_reps == 0 || h_multiplicities != nullptr, "prove_from_hints: lookup circuit needs multiplicities");
+        const uint32_t n_plain = st.g.n_witness_plain;
+        if (n_plain) {
+            ZK_REQUIRE(st.wit_maps.p != nullptr && h_witness_values != nullptr,
+                       "prove_from_hints: circuits with plain witness columns (compression modes 1-3) need zkgpu_setup_set_witness_maps "
+                       "and the witness values");
+            ZK_REQUIRE(st.max_wit_index < (int64_t)n_wits, "prove_from_hints: the witness maps reference an index >= n_wits");
+        }
+        const size_t N = st.sh.N, cells = (size_t)st.sh.NP * N, wcells = (size_t)n_plain * N;
+        zk::ArenaScope arena_scope(&ctx->c, zk::prove_scratch_bytes(st, true) + (n_vars + n_wits) * 8 + 64);
+        zk::DevBuf wit, vals, wvals;
+        wit.alloc((size_t)st.sh.W * N, ctx->c.stream);
+        vals.alloc(n_vars ? n_vars : 1, ctx->c.stream);
+        CUDA_CHECK(cudaMemcpyAsync(vals.p, h_variable_values, n_vars * 8, cudaMemcpyHostToDevice, ctx->c.stream));
+        if (st.g.lookup_reps)   // the multiplicity column is the last witness column
+            CUDA_CHECK(cudaMemcpyAsync(wit.p + (size_t)(st.sh.W - 1) * N, h_multiplicities, N * 8, cudaMemcpyHostToDevice, ctx->c.stream));
+        zk::materialize_columns_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->c.stream>>>(
+            reinterpret_cast<const uint32_t*>(st.var_maps.p), vals.p, n_vars, wit.p, cells);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->c.kernel_launches++;
+        if (n_plain) {   // plain witness columns follow the copy-permuted ones (zk_internal Shape::plain_col0 == NP)
+            wvals.alloc(n_wits ? n_wits : 1, ctx->c.stream);
+            CUDA_CHECK(cudaMemcpyAsync(wvals.p, h_witness_values, n_wits * 8, cudaMemcpyHostToDevice, ctx->c.stream));
+            zk::materialize_columns_kernel<<<(unsigned)((wcells + 255) / 256), 256, 0, ctx->c.stream>>>(
+                reinterpret_cast<const uint32_t*>(st.wit_maps.p), wvals.p, n_wits, wit.p + cells, wcells);
+            CUDA_CHECK(cudaGetLastError());
+            ctx->c.kernel_launches++;
+        }
+        zk::prove(&ctx->c, st, wit.p, h_proof_out, proof_capacity_u64);
         return 0;
     } catch (const zk::Error& e) {
         zk::g_last_error = e.what();
@@ -1013,35 +1088,11 @@ int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t
 
 int zkgpu_prove_from_variables(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
                                const uint64_t* h_multiplicities, uint64_t* h_proof_out, size_t proof_capacity_u64) {
-    try {
-        ZK_REQUIRE(ctx && s && s->s && h_variable_values && h_proof_out, "prove_from_variables: NULL argument");
-        CUDA_CHECK(cudaSetDevice(ctx->c.device));
-        const zk::Setup& st = *s->s;
-        ZK_REQUIRE(st.var_maps.p != nullptr, "prove_from_variables: call zkgpu_setup_set_variable_maps first");
-        ZK_REQUIRE(n_vars < ZKGPU_VAR_PLACEHOLDER, "prove_from_variables: too many variables");
-        ZK_REQUIRE(st.g.lookup_reps == 0 || h_multiplicities != nullptr, "prove_from_variables: lookup circuit needs multiplicities");
-        ZK_REQUIRE(st.g.n_witness_plain == 0,
-                   "prove_from_variables: circuits with plain witness columns (compression modes 1-3) also need the witness hint; use zkgpu_prove");
-        const size_t N = st.sh.N, cells = (size_t)st.sh.NP * N;
-        zk::ArenaScope arena_scope(&ctx->c, zk::prove_scratch_bytes(st, true) + n_vars * 8);
-        zk::DevBuf wit, vals;
-        wit.alloc((size_t)st.sh.W * N, ctx->c.stream);
-        vals.alloc(n_vars ? n_vars : 1, ctx->c.stream);
-        CUDA_CHECK(cudaMemcpyAsync(vals.p, h_variable_values, n_vars * 8, cudaMemcpyHostToDevice, ctx->c.stream));
-        if (st.g.lookup_reps)
-            CUDA_CHECK(cudaMemcpyAsync(wit.p + cells, h_multiplicities, N * 8, cudaMemcpyHostToDevice, ctx->c.stream));
-        zk::materialize_columns_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->c.stream>>>(
-            reinterpret_cast<const uint32_t*>(st.var_maps.p), vals.p, n_vars, wit.p, cells);
-        CUDA_CHECK(cudaGetLastError());
-        ctx->c.kernel_launches++;
-        zk::prove(&ctx->c, st, wit.p, h_proof_out, proof_capacity_u64);
-        return 0;
-    } catch (const zk::Error& e) {
-        zk::g_last_error = e.what();
-        return e.code;
-    } catch (const std::exception& e) {
-        zk::g_last_error = e.what();
-        return 99;
+    if (s && s->s && s->s->g.n_witness_plain) {
+        zk::g_last_error = "prove_from_variables: circuits with plain witness columns (compression modes 1-3) also need the witness "
+                           "hint; use zkgpu_prove_from_hints";
+        return 2;
     }
+    return zkgpu_prove_from_hints(ctx, s, h_variable_values, n_vars, nullptr, 0, h_multiplicities, h_proof_out, proof_capacity_u64);
 }
 }

@@ -165,6 +165,11 @@ def make_proof_config(log_n, fri_lde_factor=2, merkle_tree_cap_size=16, security
     return cfg
 
 
+def recursion_layer_proof_config(log_n=20):
+    """circuit_definitions/src/lib.rs:39-47 `recursion_layer_proof_config()`: lde 2, cap 16, security 100, no PoW."""
+    return make_proof_config(log_n, fri_lde_factor=2, merkle_tree_cap_size=16, security_level=100, pow_bits=0)
+
+
 def eip4844_proof_config(log_n=20):
     """circuit_definitions/src/lib.rs:49-57 `eip4844_proof_config()`: the base-layer constants."""
     return base_layer_proof_config(log_n)

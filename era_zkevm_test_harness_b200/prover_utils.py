@@ -34,12 +34,17 @@ def proof_size_u64(geo, cfg):
     return int(n)
 
 
-def synth_trace(geo, seed=0, pinned=False, witness_seed=None):
+def synth_trace(geo, seed=0, pinned=False, witness_seed=None, out_witness=None):
     """Synthetic satisfying trace (stands in for Rust synthesis): returns (witness_cols [W,n], setup_cols [S,n]) uint64.
-    With `witness_seed`, `seed` fixes the circuit type (setup columns) and `witness_seed` the instance (witness columns)."""
+    With `witness_seed`, `seed` fixes the circuit type (setup columns) and `witness_seed` the instance (witness columns).
+    `out_witness`: a caller-owned (e.g. pinned, PinnedPool) uint64 buffer of at least W*n words to generate the witness into."""
     lib = _lib.load()
     n = 1 << geo.log_n
-    if pinned:
+    if out_witness is not None:
+        assert out_witness.dtype == np.uint64 and out_witness.flags.c_contiguous and out_witness.size >= geo.n_witness * n
+        wit = out_witness.reshape(-1)[: geo.n_witness * n].reshape(geo.n_witness, n)
+        setup = np.empty((geo.n_setup, n), dtype=np.uint64)
+    elif pinned:
         import torch
         wit_t = torch.empty((geo.n_witness, n), dtype=torch.int64).pin_memory()
         set_t = torch.empty((geo.n_setup, n), dtype=torch.int64).pin_memory()
@@ -52,6 +57,34 @@ def synth_trace(geo, seed=0, pinned=False, witness_seed=None):
     else:
         _lib.check(lib.zkgpu_synth_trace_instance(ctypes.byref(geo), seed, witness_seed, _p(wit), _p(setup)))
     return wit, setup
+
+
+class PinnedPool:
+    """A few page-locked host buffers (zkgpu_host_alloc = cudaHostAlloc) of one size, handed out and taken back: witness
+    columns generated into them upload at full PCIe speed and asynchronously (zkgpu_witness_stage)."""
+
+    def __init__(self, n_buffers, n_u64):
+        import queue
+        self.lib = _lib.load()
+        self.n_u64 = int(n_u64)
+        self.ptrs, self.free = [], queue.Queue()
+        for _ in range(n_buffers):
+            p = self.lib.zkgpu_host_alloc(self.n_u64 * 8)
+            if not p:
+                raise _lib.ZkGpuError("zkgpu_host_alloc failed: " + self.lib.zkgpu_last_error().decode())
+            self.ptrs.append(p)
+            self.free.put(np.ctypeslib.as_array((ctypes.c_uint64 * self.n_u64).from_address(p)))
+
+    def take(self):
+        return self.free.get()      # blocks until a buffer is handed back
+
+    def give(self, buf):
+        self.free.put(buf)
+
+    def close(self):
+        for p in self.ptrs:
+            self.lib.zkgpu_host_free(p)
+        self.ptrs = []
 
 
 class SetupData:
@@ -82,10 +115,22 @@ def create_setup_data(ctx, geo: Geometry, cfg: ProofConfig, setup_cols):
     return SetupData(ctx, geo, cfg, h, vk_cap)
 
 
+def _proof_buffer(setup, proof_out):
+    """-> (buffer, capacity in u64).  A caller-supplied buffer must be a C-contiguous uint64 array able to hold the proof: the
+    library writes `zkgpu_proof_size_u64` words into it and is told the buffer's real size."""
+    n_u64 = proof_size_u64(setup.geo, setup.cfg)
+    if proof_out is None:
+        return np.empty(n_u64, dtype=np.uint64), n_u64
+    if not (isinstance(proof_out, np.ndarray) and proof_out.dtype == np.uint64 and proof_out.flags.c_contiguous and proof_out.ndim == 1):
+        raise ValueError("proof_out must be a one-dimensional C-contiguous numpy uint64 array")
+    if proof_out.size < n_u64:
+        raise ValueError(f"proof_out holds {proof_out.size} u64, the proof needs {n_u64}")
+    return proof_out, int(proof_out.size)
+
+
 def prove_circuit(ctx, setup: SetupData, witness_cols, proof_out=None):
     """witness_cols: numpy uint64 [W, n] (host) or a torch CUDA int64 tensor [W, n] (already resident)."""
-    n_u64 = proof_size_u64(setup.geo, setup.cfg)
-    proof = np.empty(n_u64, dtype=np.uint64) if proof_out is None else proof_out
+    proof, n_u64 = _proof_buffer(setup, proof_out)
     if isinstance(witness_cols, np.ndarray):
         w = np.ascontiguousarray(witness_cols, dtype=np.uint64)
         assert w.shape == (setup.geo.n_witness, 1 << setup.geo.log_n), w.shape
@@ -106,8 +151,7 @@ def stage_witness(ctx, setup: SetupData, witness_cols, slot):
 
 
 def prove_staged(ctx, setup: SetupData, slot, proof_out=None):
-    n_u64 = proof_size_u64(setup.geo, setup.cfg)
-    proof = np.empty(n_u64, dtype=np.uint64) if proof_out is None else proof_out
+    proof, n_u64 = _proof_buffer(setup, proof_out)
     _lib.check(ctx.lib.zkgpu_prove_staged(ctx.h, setup.handle, slot, _p(proof), n_u64))
     return proof
 
@@ -120,11 +164,31 @@ def set_variable_maps(ctx, setup: SetupData, var_maps):
     _lib.check(ctx.lib.zkgpu_setup_set_variable_maps(ctx.h, setup.handle, _p(m)))
 
 
-def prove_from_variables(ctx, setup: SetupData, variable_values, multiplicities=None, proof_out=None):
+def set_witness_maps(ctx, setup: SetupData, wit_maps):
+    """wit_maps: uint32 [n_witness_plain, n] -- `DenseWitnessCopyHint` of the circuit type (row -> index into the assembly's
+    witness values per plain witness column; compression modes 1-3).  Uploaded once per setup; see prove_from_hints."""
+    m = np.ascontiguousarray(wit_maps, dtype=np.uint32)
+    assert m.shape == (setup.geo.n_witness_plain, 1 << setup.geo.log_n), m.shape
+    _lib.check(ctx.lib.zkgpu_setup_set_witness_maps(ctx.h, setup.handle, _p(m)))
+
+
+def prove_from_hints(ctx, setup: SetupData, variable_values, witness_values=None, multiplicities=None, proof_out=None):
     """The reference's hand-off (prove_from_precomputations(.., vars_hint, wits_hint, ..), src/prover_utils.rs:338-348): ship the
-    assembly's variable values (+ lookup multiplicities), gather the trace columns on the GPU, prove."""
-    n_u64 = proof_size_u64(setup.geo, setup.cfg)
-    proof = np.empty(n_u64, dtype=np.uint64) if proof_out is None else proof_out
+    assembly's variable values, witness values (circuits with plain witness columns) and lookup multiplicities; the trace
+    columns are gathered on the GPU through the resident maps, then proven."""
+    proof, n_u64 = _proof_buffer(setup, proof_out)
+    v = np.ascontiguousarray(variable_values, dtype=np.uint64)
+    wv = None if witness_values is None else np.ascontiguousarray(witness_values, dtype=np.uint64)
+    mp = None if multiplicities is None else np.ascontiguousarray(multiplicities, dtype=np.uint64)
+    null = ctypes.c_void_p(0)
+    _lib.check(ctx.lib.zkgpu_prove_from_hints(ctx.h, setup.handle, _p(v), v.size, _p(wv) if wv is not None else null,
+                                              0 if wv is None else wv.size, _p(mp) if mp is not None else null, _p(proof), n_u64))
+    return proof
+
+
+def prove_from_variables(ctx, setup: SetupData, variable_values, multiplicities=None, proof_out=None):
+    """prove_from_hints for circuits without plain witness columns (every base- and recursion-layer circuit)."""
+    proof, n_u64 = _proof_buffer(setup, proof_out)
     v = np.ascontiguousarray(variable_values, dtype=np.uint64)
     mp = None if multiplicities is None else np.ascontiguousarray(multiplicities, dtype=np.uint64)
     _lib.check(ctx.lib.zkgpu_prove_from_variables(ctx.h, setup.handle, _p(v), v.size, _p(mp) if mp is not None else ctypes.c_void_p(0),

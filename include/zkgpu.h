@@ -196,6 +196,17 @@ ZKGPU_API int zkgpu_setup_set_variable_maps(zkgpu_ctx* ctx, zkgpu_setup* s, cons
  * circuit has no lookup) -- boojum keeps them in the assembly next to the variable values.  GPU: gather -> columns -> prove. */
 ZKGPU_API int zkgpu_prove_from_variables(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
                                          const uint64_t* h_multiplicities, uint64_t* h_proof_out, size_t proof_capacity_u64);
+/* The second hint of the same call: `wits_hint: &DenseWitnessCopyHint` (src/prover_utils.rs:347) -- per plain witness column (the
+ * columns NOT under the copy permutation: compression modes 1-3 have 78 / 74 / 62 of them) a dense map row -> index into the
+ * assembly's witness-value array.  h_wit_maps: n_witness_plain x 2^log_n u32, column-major, ZKGPU_VAR_PLACEHOLDER = 0.
+ * Both setters reject nothing by themselves; the largest index of each map is remembered and checked against n_vars / n_wits
+ * by the prove calls (an out-of-range index is an error, not a silent zero). */
+ZKGPU_API int zkgpu_setup_set_witness_maps(zkgpu_ctx* ctx, zkgpu_setup* s, const uint32_t* h_wit_maps);
+/* zkgpu_prove_from_variables plus the witness values behind the plain witness columns (h_witness_values may be NULL iff the
+ * circuit has no plain witness columns). */
+ZKGPU_API int zkgpu_prove_from_hints(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_variable_values, size_t n_vars,
+                                     const uint64_t* h_witness_values, size_t n_wits, const uint64_t* h_multiplicities,
+                                     uint64_t* h_proof_out, size_t proof_capacity_u64);
 
 /* Verifier::verify (src/prover_utils.rs:351-372): CPU only, as in the reference. Returns 0 iff the proof is valid,
  * 1 if invalid (message says which check failed), >1 on malformed input. */

@@ -101,11 +101,13 @@ def _worker(rank, world, port, out_dir):
                         security_level=4)
     if rank == 0:
         assert len(res["proofs"]) == plan.n_jobs
-        files = sorted(os.path.relpath(os.path.join(d, f), out_dir) for d, _, fs in os.walk(out_dir) for f in fs)
+        syn = os.path.join(out_dir, "synthetic")   # the reference's layout, under synthetic/ with a manifest (block.synthetic_root)
+        assert os.path.exists(os.path.join(syn, "SYNTHETIC.json"))
+        files = sorted(os.path.relpath(os.path.join(d, f), syn) for d, _, fs in os.walk(syn) for f in fs)
         assert "recursion_layer/scheduler_proof.json" in files and "aux_layer/compression_proof_1.json" in files
         assert "base_layer/basic_circuit_proof_1_4.json" in files and "recursion_layer/node_layer_proof_3_1_0.json" in files
         # the file is the reference's externally tagged JSON and loads back to the same flat proof
-        flat, variant = proof_format.load_proof_json(os.path.join(out_dir, "base_layer/basic_circuit_proof_8_1.json"))
+        flat, variant = proof_format.load_proof_json(os.path.join(syn, "base_layer/basic_circuit_proof_8_1.json"))
         assert variant == "RAMPermutation" and (flat == res["proofs"]["base_layer/basic_circuit_proof_8_1.json"]).all()
         # two instances of one circuit type: same VK, different proofs
         a, b = res["proofs"]["base_layer/basic_circuit_proof_1_0.json"], res["proofs"]["base_layer/basic_circuit_proof_1_1.json"]

@@ -143,6 +143,50 @@ def test_prove_from_variables_matches_column_path(gpu, oracle):
     sd.close()
 
 
+def test_prove_from_hints_with_plain_witness_columns(gpu, oracle):
+    """Compression-mode-1 shape (52 copy + boolean column + 78 plain witness columns): both hints of the reference's hand-off --
+    DenseVariablesCopyHint for the copy-permuted columns, DenseWitnessCopyHint for the plain witness columns -- give the proof
+    of the column path, bit for bit; an index past the value array is an error, not a silent zero."""
+    import json
+    import os
+    fixture = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
+    geo, cfg = [(g, c) for k, g, c, _ in G.compression_geometries_from_fixture(fixture) if k == "compression_1"][0]
+    geo = geo.scaled(8)
+    cfg = G.make_proof_config(8, 1 << cfg.log_lde, cfg.cap_size, security_level=4 * cfg.log_lde)
+    wit, setup = PU.synth_trace(geo, seed=23)
+    n, npm, npl = 1 << geo.log_n, geo.n_perm, geo.n_witness_plain
+    assert npl == 78 and wit.shape[0] == npm + npl
+    rng = np.random.default_rng(9)
+
+    def to_maps(cells):
+        uniq, inverse = np.unique(cells, return_inverse=True)
+        perm = rng.permutation(uniq.size)
+        values = np.empty_like(uniq)
+        values[perm] = uniq
+        maps = perm[inverse].astype(np.uint32)
+        maps[cells == 0] = np.uint32(0xFFFFFFFF)
+        return values, maps
+
+    var_values, var_maps = to_maps(wit[:npm].reshape(-1))
+    wit_values, wit_maps = to_maps(wit[npm:npm + npl].reshape(-1))
+    sd = PU.create_setup_data(gpu, geo, cfg, setup)
+    PU.set_variable_maps(gpu, sd, var_maps.reshape(npm, n))
+    PU.set_witness_maps(gpu, sd, wit_maps.reshape(npl, n))
+    got = PU.prove_from_hints(gpu, sd, var_values, wit_values)
+    assert (got == PU.prove_circuit(gpu, sd, wit)).all()
+    assert (got == oracle.prove(geo, cfg, wit, setup)).all()
+    from era_zkevm_test_harness_b200 import ZkGpuError
+    with pytest.raises(ZkGpuError, match="n_wits"):
+        PU.prove_from_hints(gpu, sd, var_values, wit_values[: int(wit_maps[wit_maps != 0xFFFFFFFF].max())])
+    with pytest.raises(ZkGpuError, match="n_vars"):
+        PU.prove_from_hints(gpu, sd, var_values[: int(var_maps[var_maps != 0xFFFFFFFF].max())], wit_values)
+    with pytest.raises(ZkGpuError, match="plain witness"):
+        PU.prove_from_variables(gpu, sd, var_values)
+    with pytest.raises(ValueError):
+        PU.prove_circuit(gpu, sd, wit, proof_out=np.empty(16, dtype=np.uint64))
+    sd.close()
+
+
 def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
     """compute_setups mirror: one VK JSON per circuit type under the reference's file names; the cap in each file is the
     oracle's commitment of the same setup columns, the geometry read back from the file is the one that was committed."""
@@ -152,8 +196,10 @@ def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
     paths = CS.generate_base_layer_vks(gpu, str(tmp_path), fx, log_n=9)
     paths.update(CS.generate_recursive_layer_vks(gpu, str(tmp_path), fx, log_n=9))
-    assert sorted(os.listdir(tmp_path / "base_layer")) == sorted(f"vk_{t}.json" for t in range(1, 14))
-    assert sorted(os.listdir(tmp_path / "recursion_layer")) == ["vk_1.json", "vk_3.json", "vk_node.json"]
+    # the reference's file names, under <root>/synthetic/ with a manifest: synthetic setup columns + unpinned hash
+    assert os.path.exists(tmp_path / "synthetic" / "SYNTHETIC.json")
+    assert sorted(os.listdir(tmp_path / "synthetic" / "base_layer")) == sorted(f"vk_{t}.json" for t in range(1, 14))
+    assert sorted(os.listdir(tmp_path / "synthetic" / "recursion_layer")) == ["vk_1.json", "vk_3.json", "vk_node.json"]
     for t in (1, 8, 10):
         (variant, vk), = json.load(open(paths[t])).items()
         assert variant == fx["base"][str(t)]["variant"] and vk["fixed_parameters"]["domain_size"] == 512
@@ -161,6 +207,35 @@ def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
         cfg = G.base_layer_proof_config(9)
         setup = PU.synth_trace(geo, seed=0x5E7)[1]
         assert (np.array(vk["setup_merkle_tree_cap"], dtype=np.uint64) == oracle.setup_cap(geo, cfg, setup)).all()
+
+
+def test_recursive_layer_vks_and_proofs_self_check(gpu, oracle, tmp_path):
+    """generate_recursive_layer_vks_and_proofs (compute_setups.rs:439-586): each recursion-layer circuit type is set up, proven
+    once with a placeholder witness and the proof verified against the fresh VK before anything is written; the stored proof
+    loads back and is accepted by BOTH verifiers; a witness that does not fit the setup aborts the run."""
+    import json
+    import os
+    from era_zkevm_test_harness_b200 import compute_setups as CS, proof_format
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
+    out = CS.generate_recursive_layer_vks_and_proofs(gpu, str(tmp_path), fx, log_n=9)
+    assert set(out) == {"scheduler", "leaf_3", "node"}
+    for key, rec in out.items():
+        (variant, vk), = json.load(open(rec["vk"])).items()
+        geo = G.geometry_from_vk(vk, G.RECURSION_GATE_ORDER)
+        cfg = G.recursion_layer_proof_config(9)
+        flat, _ = proof_format.load_proof_json(rec["proof"])
+        cap = np.array(vk["setup_merkle_tree_cap"], dtype=np.uint64)
+        ok, msg = PU.verify_proof(geo, cfg, cap, flat)
+        assert ok, msg
+        ok, msg = oracle.verify(geo, cfg, cap, flat)
+        assert ok, msg
+
+    def broken(geo):
+        w = PU.synth_trace(geo, seed=0x5E7)[0]
+        w[2, 3] ^= np.uint64(1)
+        return w
+    with pytest.raises(RuntimeError, match="does not verify"):
+        CS.generate_recursive_layer_vks_and_proofs(gpu, str(tmp_path / "bad"), fx, log_n=9, witness_source=broken)
 
 
 def test_staged_witness_upload_gives_the_same_proofs(gpu):
