@@ -25,7 +25,32 @@ static __constant__ uint32_t gl_eps_opaque_c = 0xFFFFFFFFu;
 
 namespace gl {
 
-GL_HD uint64_t canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+// x mod p for any u64 x.  Device: x + (2^32 - 1) carries out exactly when x >= p and then IS x - p (mod 2^64); the carry
+// predicate of the add drives the two selects directly -- IADD3, IADD3.X, SEL, SEL: 4 alu-pipe instructions against the 6 of the
+// compare form (2 ISETP + 2 IADD3 + 2 SEL).  (The variant that applies the carry with an IMAD.WIDE -- 1 instruction fewer, but on
+// the fma pipe -- measured 1 % SLOWER on the whole proof: the multiply pipe is the contended one.)
+// Measured per kernel (ncu time of one MainVM proof, profiles/r02_*): quotient_perm -2.8 %, quotient_gates -2 %, NTT pass B -3 %,
+// but NTT pass A +6 % (it sits on its 128-register limit and spills more), so ntt1024.cu keeps the compare form (ZK_CANON_SEL 0).
+#ifndef ZK_CANON_SEL
+#define ZK_CANON_SEL 1
+#endif
+GL_HD uint64_t canon(uint64_t x) {
+#if defined(__CUDA_ARCH__) && ZK_CANON_SEL
+    uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), r0, r1;
+    asm("{\n\t.reg .u32 t0,t1,k;\n\t.reg .pred q;\n\t"
+        "add.cc.u32 t0, %2, 0xffffffff;\n\t"
+        "addc.cc.u32 t1, %3, 0;\n\t"
+        "addc.u32 k, 0, 0;\n\t"
+        "setp.ne.u32 q, k, 0;\n\t"
+        "selp.u32 %0, t0, %2, q;\n\t"
+        "selp.u32 %1, t1, %3, q;\n\t}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(x0), "r"(x1));
+    return ((uint64_t)r1 << 32) | r0;
+#else
+    return x >= GL_P ? x - GL_P : x;
+#endif
+}
 
 // canonical add/sub.  Device: PTX borrow chains (sub = 4 alu + 1 fma SASS instructions, add = 5 alu + 2 fma) instead of the
 // 64-bit compare + select sequences the C form compiles to (9 each).

@@ -14,7 +14,7 @@
 
 namespace glx {
 
-GL_HD uint64_t canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+GL_HD uint64_t canon(uint64_t x) { return gl::canon(x); }
 
 // a * b mod p for any u64 a, b; result in [0, 2^64), not canonical.
 //   a*b = lo + 2^64*hl + 2^96*hh,  2^64 = 2^32 - 1,  2^96 = -1 (mod p)

@@ -12,6 +12,7 @@
 // inverse: natural evaluations -> natural monomials (second pass writes transposed).
 // General multiplications per element: 3 in pass A (coset pre-scale by a per-b constant, 32x32 twiddle, inter-pass factor),
 // 1 in pass B; everything else is add/sub and shifts.
+#define ZK_CANON_SEL 0   // see gl.cuh canon(): the select form costs pass A more in spills than it saves
 #include "ntt1024_core.cuh"
 #include <mutex>
 #include "zk_internal.cuh"
