@@ -520,7 +520,7 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
     const uint64_t omega_ln = gl::omega(log_ln);
     const uint64_t* q = queries;
     for (uint32_t qi = 0; qi < cfg.n_queries; qi++) {
-        size_t idx = (size_t)(tr.challenge() & (uint64_t)(sh.LN - 1));
+        size_t idx = tr.query_index(ilog2(sh.LN));
         const uint64_t* leaf_w = q; q += sh.W; const uint64_t* path_w = q; q += sh.depth * 4;
         const uint64_t* leaf_2 = q; q += sh.S2; const uint64_t* path_2 = q; q += sh.depth * 4;
         const uint64_t* leaf_q = q; q += sh.Q; const uint64_t* path_q = q; q += sh.depth * 4;

@@ -60,10 +60,18 @@ void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
 
 constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;
 
+// boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, Poseidon2Goldilocks> [recalled; not observable without the hash]:
+// witnessed elements are buffered; a challenge request absorbs the buffer (rate 8, overwrite, zero padding, one permutation
+// per block) and the sponge's COMMITMENT -- the first 4 state lanes -- becomes the list of available challenges; when that list
+// runs out the state is permuted once more.  Query indexes come from a bit buffer (`BoolsBuffer`): every challenge contributes
+// its 64 - log2(LDE domain) low bits, LSB first, and an index takes log2(LDE domain) of them.
 struct Transcript {
+    static constexpr int CHALLENGES_PER_PERMUTATION = 4;   // = capacity / digest width CW
     uint64_t st[12] = {0};
     std::vector<uint64_t> buf;
-    int pos = 8;
+    int pos = CHALLENGES_PER_PERMUTATION;
+    uint64_t bitbuf = 0;
+    int nbits = 0;
     void absorb(const uint64_t* v, size_t n) { buf.insert(buf.end(), v, v + n); }
     void absorb(const gl::e2& e) { buf.push_back(e.c0); buf.push_back(e.c1); }
     uint64_t challenge() {
@@ -74,11 +82,23 @@ struct Transcript {
             }
             buf.clear();
             pos = 0;
-        } else if (pos == 8) {
+        } else if (pos == CHALLENGES_PER_PERMUTATION) {
             host_poseidon2_permute(st);
             pos = 0;
         }
         return st[pos++];
+    }
+    size_t query_index(uint32_t bits) {   // bits = log2(LDE domain) <= 32
+        const int take = 64 - (int)bits;
+        while (nbits < (int)bits) {
+            const uint64_t c = challenge();
+            bitbuf |= (take == 64 ? c : (c & (((uint64_t)1 << take) - 1))) << nbits;   // nbits < bits, so nbits + take <= 63
+            nbits += take;
+        }
+        const size_t idx = (size_t)(bitbuf & (((uint64_t)1 << bits) - 1));
+        bitbuf >>= bits;
+        nbits -= (int)bits;
+        return idx;
     }
     gl::e2 challenge_ext() { uint64_t a = challenge(); uint64_t b = challenge(); return gl::make2(a, b); }
 };

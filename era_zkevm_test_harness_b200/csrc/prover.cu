@@ -803,7 +803,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         for (uint32_t k = 0; k < NF; k++) per_q += 2 * ((size_t)1 << cfg.fri_schedule[k]) + sh.fri_depth[k] * 4;
         std::vector<uint32_t> idx((size_t)NQ * (NF + 1));
         for (uint32_t q = 0; q < NQ; q++) {
-            size_t di = (size_t)(tr.challenge() & (uint64_t)(LN - 1));
+            size_t di = tr.query_index(ilog2(LN));
             idx[q] = (uint32_t)di;
             for (uint32_t k = 0; k < NF; k++) { di >>= cfg.fri_schedule[k]; idx[(size_t)(k + 1) * NQ + q] = (uint32_t)di; }
         }

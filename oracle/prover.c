@@ -120,14 +120,21 @@ EXPORT void orc_deep_at_point(const zkgpu_geometry *g, const uint64_t *wl, const
     free(src); free(phip);
 }
 
-/* ------------------------------------------------------------------ transcript (Poseidon2 sponge, rate 8, overwrite) */
+/* ------------------------------------------------------------------ transcript (Poseidon2 sponge, rate 8, overwrite)
+ * boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, R> [recalled; not observable without the hash]: witnessed elements are
+ * buffered; a challenge request absorbs the buffer (zero padding, one permutation per block of 8) and the sponge's commitment
+ * -- the first TR_CHALLENGES = 4 lanes -- becomes the list of available challenges; when it runs out the state is permuted again.
+ * Query indexes (`BoolsBuffer`): every challenge contributes its 64 - log2(LDE domain) low bits, LSB first. */
+#define TR_CHALLENGES 4
 typedef struct {
     uint64_t st[12];
     uint64_t *buf;
     size_t len, capacity;
-    int pos; /* next rate lane to hand out; 8 = exhausted */
+    int pos; /* next lane to hand out; TR_CHALLENGES = exhausted */
+    uint64_t bitbuf;
+    int nbits;
 } tr_t;
-static void tr_init(tr_t *t) { memset(t, 0, sizeof(*t)); t->pos = 8; }
+static void tr_init(tr_t *t) { memset(t, 0, sizeof(*t)); t->pos = TR_CHALLENGES; }
 static void tr_free(tr_t *t) { free(t->buf); }
 static void tr_absorb(tr_t *t, const uint64_t *v, size_t n) {
     if (t->len + n > t->capacity) {
@@ -145,11 +152,23 @@ static uint64_t tr_challenge(tr_t *t) {
         }
         t->len = 0;
         t->pos = 0;
-    } else if (t->pos == 8) {
+    } else if (t->pos == TR_CHALLENGES) {
         orc_poseidon2_permute(t->st);
         t->pos = 0;
     }
     return t->st[t->pos++];
+}
+static size_t tr_query_index(tr_t *t, uint32_t bits) {
+    const int take = 64 - (int)bits;
+    while (t->nbits < (int)bits) {
+        const uint64_t c = tr_challenge(t);
+        t->bitbuf |= (take == 64 ? c : (c & (((uint64_t)1 << take) - 1))) << t->nbits;
+        t->nbits += take;
+    }
+    const size_t idx = (size_t)(t->bitbuf & (((uint64_t)1 << bits) - 1));
+    t->bitbuf >>= bits;
+    t->nbits -= (int)bits;
+    return idx;
 }
 static gl2 tr_challenge_ext(tr_t *t) { uint64_t a = tr_challenge(t); uint64_t b = tr_challenge(t); return gl2_make(a, b); }
 
@@ -588,7 +607,7 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
         p += sh.fri_cap[k] * 4;
     }
     for (uint32_t q = 0; q < cfg->n_queries; q++) {
-        size_t idx = (size_t)(tr_challenge(&tr) & (uint64_t)(LN - 1));
+        size_t idx = tr_query_index(&tr, (uint32_t)(log_n + log_lde));
         const uint64_t *ldes[4] = {lde_w, lde_2, lde_q, lde_s};
         const uint64_t *trees[4] = {tree_w, tree_2, tree_q, tree_s};
         const uint32_t widths[4] = {W, S2, Q, S};
@@ -655,7 +674,7 @@ EXPORT int orc_verify(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     shape_t sh; make_shape(g, cfg, &sh);
     const uint32_t W = sh.W, S = sh.S, S2 = sh.S2, Q = sh.Q, NP = n_perm(g), C = n_chunks(g), E2 = n_s2_ext(g), QD = g->quotient_degree;
     const uint32_t n_at_z = sh.n_at_z, n_at_0 = sh.n_at_0, NF = cfg->n_fri_oracles;
-    const size_t N = sh.N, LN = sh.LN, cap = cfg->cap_size;
+    const size_t N = sh.N, cap = cfg->cap_size;
     const int log_n = g->log_n, log_ln = log_n + cfg->log_lde;
     const uint64_t omega = gl_omega(log_n);
     open_src *src = NULL; gl2 *wz = NULL, *sz = NULL, *ez = NULL, *qz = NULL, *phip = NULL; uint64_t *scratch = NULL, *cells = NULL;
@@ -819,7 +838,7 @@ EXPORT int orc_verify(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
         const uint64_t omega_ln = gl_omega(log_ln);
         const uint64_t *qp = queries;
         for (uint32_t q = 0; q < cfg->n_queries; q++) {
-            const size_t idx = (size_t)(tr_challenge(&tr) & (uint64_t)(LN - 1));
+            const size_t idx = tr_query_index(&tr, (uint32_t)log_ln);
             const uint64_t *leaf[4], *caps[4] = {cap_w, cap_2, cap_q, vk_cap};
             const uint32_t widths[4] = {W, S2, Q, S};
             static const char *names[4] = {"witness", "stage 2", "quotient", "setup"};

@@ -36,6 +36,11 @@ __global__ void k(uint32_t* out, uint32_t seed) {
             if (OP == 16) asm volatile("sub.cc.u32 %0, %0, %2;\n\tsubc.u32 %1, %1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // 64-bit sub
             if (OP == 17) asm volatile("add.u64 %0, %0, %1;" : "+l"(w[i]) : "l"(((uint64_t)b[i] << 32) | a[i]));   // 64-bit add (compiler form)
             if (OP == 18) asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w[i]) : "r"(a[i] ^ (uint32_t)w[i]), "r"(b[i]));  // IMAD.WIDE no addend (+xor)
+            if (OP == 19) asm volatile("{.reg .pred q; setp.lt.u32 q, %0, %1; selp.u32 %0, %2, %0, q;}" : "+r"(a[i]) : "r"(b[i]), "r"(seed));  // ISETP + SEL (3 operands)
+            if (OP == 20) asm volatile("{.reg .pred q; setp.lt.u32 q, %1, %2; selp.u32 %0, %2, %0, q; selp.u32 %1, %0, %1, q;}" : "+r"(a[i]), "+r"(b[i]) : "r"(seed));  // ISETP + 2 SEL
+            if (OP == 21) asm volatile("{.reg .pred q; setp.lt.u32 q, %1, %2; setp.lt.and.u32 q, %0, %2, q; selp.u32 %0, %2, %0, q;}" : "+r"(a[i]), "+r"(b[i]) : "r"(seed));  // 2 ISETP + SEL
+            if (OP == 22) asm volatile("add.cc.u32 %0, %0, %2;\n\tmadc.lo.u32 %1, %1, 1, %3;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // IADD3 + IMAD.X?
+            if (OP == 23) asm volatile("mov.b32 %0, %1;" : "=r"(a[i]) : "r"(b[i] + it));   // MOV-ish
             if (OP == 8) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(a[i]), "+r"(b[i]) : "r"(seed), "r"(it)); // fused wide w/ carry
         }
     }
@@ -78,6 +83,10 @@ int main() {
     run<6>("1 IMAD + 1 add", 2);
     run<7>("SHF", 1);
     run<8>("mad.lo.cc+madc.hi (fused?)", 2);
+    run<19>("ISETP + SEL (3 operands)", 2);
+    run<20>("ISETP + 2 SEL", 3);
+    run<21>("2 ISETP + SEL", 3);
+    run<22>("add.cc + madc.lo (IADD3+IMAD.X?)", 2);
     run<9>("IADD3.X alone (addc)", 1);
     run<10>("ISETP+SEL", 2);
     run<11>("LOP3", 1);
