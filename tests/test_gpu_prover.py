@@ -278,3 +278,47 @@ def test_pinned_host_buffers_from_the_library(gpu):
     del pinned
     gpu.lib.zkgpu_host_free(ptr)
     sd.close()
+
+
+def test_gpu_block_prover_staged_path_matches_oracle(gpu, oracle, tmp_path):
+    """The block workflow on the GPU (block.GpuBlockProver: witnesses generated into pinned buffers on host threads, staged upload
+    with look-ahead, LRU of resident setups) on a small synthetic block -- base (two types, several instances) -> leaf -> node ->
+    scheduler -> compression mode 1: every proof equals the oracle's proof of the same trace word for word, is accepted by both
+    verifiers, and lands under <out>/synthetic/ in the reference's file layout."""
+    import json
+    import os
+    from era_zkevm_test_harness_b200 import block as B, proof_format
+    fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
+    table, base_keys, leaf_keys, node_key, sched_key = B.circuit_table(fx, log_n=8, compression_log_n=6)
+    table = {k: (g, c if k.startswith("compression_") else G.make_proof_config(g.log_n, 2, 16, security_level=6)) for k, (g, c) in table.items()}
+    plan = B.plan_block({1: 3, 8: 2}, base_keys, leaf_keys, node_key, sched_key, arity=2, compression_modes=(1,))
+    prover = B.GpuBlockProver(gpu, table, max_resident=3, setup_seed=77, host_threads=4)
+    checked = []
+
+    def verify(job, proof):
+        geo, cfg = table[job.geometry_key]
+        cap = prover.vk_caps.get(job.geometry_key)
+        if cap is None:
+            cap = prover.setup(job.geometry_key).vk_cap.copy()
+        ok1, _ = PU.verify_proof(geo, cfg, cap, proof)
+        ok2, _ = oracle.verify(geo, cfg, cap, proof)
+        checked.append(job.file)
+        return ok1 and ok2
+
+    seeds = {}
+
+    def prove(job, seed):
+        seeds[job.file] = seed
+        return prover.prove(job, seed)
+
+    res = B.prove_block(plan, prove, block_seed=3, out_dir=str(tmp_path), verify=verify, prefetch=prover.prefetch, security_level=6)
+    assert len(res["proofs"]) == plan.n_jobs == len(checked)
+    for _, jobs in plan.stages:
+        for job in jobs[:2]:     # the oracle on the same trace: same setup seed, the job's witness seed
+            geo, cfg = table[job.geometry_key]
+            wit, setup = PU.synth_trace(geo, seed=77, witness_seed=seeds[job.file])
+            assert (res["proofs"][job.file] == oracle.prove(geo, cfg, wit, setup)).all(), job.file
+    flat, variant = proof_format.load_proof_json(str(tmp_path / "synthetic" / "recursion_layer" / "scheduler_proof.json"))
+    assert variant == "SchedulerCircuit" and (flat == res["proofs"]["recursion_layer/scheduler_proof.json"]).all()
+    assert os.path.exists(tmp_path / "synthetic" / "SYNTHETIC.json")
+    prover.close()
