@@ -64,6 +64,53 @@ GL_HD uint64_t mul(uint64_t a, uint64_t b) {
 }
 GL_HD uint64_t sqr(uint64_t a) { return mul(a, a); }
 
+// a * b + c mod p for any u64 a, b, c; result in [0, 2^64), not canonical.  The addend rides in the accumulator of the first wide
+// product and its carry joins the 2^64 column: three instructions more than mul().
+GL_HD uint64_t fma(uint64_t a, uint64_t b, uint64_t c) {
+#ifdef __CUDA_ARCH__
+    uint32_t a0 = (uint32_t)a, a1 = (uint32_t)(a >> 32), b0 = (uint32_t)b, b1 = (uint32_t)(b >> 32), c0 = (uint32_t)c, c1 = (uint32_t)(c >> 32);
+    uint32_t r0, r1;
+    asm("{\n\t"
+        ".reg .u32 l0,l1,h0,h1,k,c,cy;\n\t"
+        "mad.lo.cc.u32 l0, %2, %4, %7;\n\t"
+        "madc.hi.cc.u32 l1, %2, %4, %8;\n\t"
+        "addc.u32 cy, 0, 0;\n\t"
+        "mad.lo.cc.u32 l1, %2, %5, l1;\n\t"
+        "madc.hi.u32 h0, %2, %5, 0;\n\t"
+        "mad.lo.cc.u32 l1, %3, %4, l1;\n\t"
+        "madc.hi.cc.u32 h0, %3, %4, h0;\n\t"
+        "addc.u32 h1, 0, 0;\n\t"
+        "add.cc.u32 h0, h0, cy;\n\t"     // the addend's carry enters the 2^64 column here (hi(a0*b1) + 2 carries could wrap)
+        "addc.u32 h1, h1, 0;\n\t"
+        "mad.lo.cc.u32 h0, %3, %5, h0;\n\t"
+        "madc.hi.u32 h1, %3, %5, h1;\n\t"
+        "sub.cc.u32 l0, l0, h1;\n\t"
+        "subc.cc.u32 l1, l1, 0;\n\t"
+        "subc.u32 k, 0, 0;\n\t"
+        "sub.cc.u32 l0, l0, k;\n\t"
+        "subc.u32 l1, l1, 0;\n\t"
+        "mad.lo.cc.u32 l0, h0, %6, l0;\n\t"
+        "madc.hi.cc.u32 l1, h0, %6, l1;\n\t"
+        "addc.u32 c, 0, 0;\n\t"
+        "mad.lo.cc.u32 %0, c, %6, l0;\n\t"
+        "madc.hi.u32 %1, c, %6, l1;\n\t"
+        "}"
+        : "=r"(r0), "=r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(GL_EPS_OPAQUE), "r"(c0), "r"(c1));
+    return ((uint64_t)r1 << 32) | r0;
+#else
+    unsigned __int128 x = (unsigned __int128)a * b + c;
+    uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+    uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+    uint64_t t = lo - hh;
+    if (lo < hh) t -= GL_EPS;
+    uint64_t m = hl * GL_EPS;
+    uint64_t r = t + m;
+    if (r < t) r += GL_EPS;
+    return r;
+#endif
+}
+
 // lo + 2^64*hi mod p for a small hi (< 2^32): one multiply-add with carry fix-up.  Not canonical.
 GL_HD uint64_t reduce96(uint64_t lo, uint32_t hi) {
 #ifdef __CUDA_ARCH__

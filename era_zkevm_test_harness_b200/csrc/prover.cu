@@ -15,6 +15,7 @@
 #include "host_common.cuh"
 #include "quotient.cuh"
 #include "dot.cuh"
+#include "glx.cuh"
 
 namespace zk {
 
@@ -177,10 +178,9 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
             dsuf[j] = suf;  // product of D_l for l > j
             gl::e2 d = gl::make2(1, 0);
             for (uint32_t i = j * p.QD; i < (j + 1) * p.QD && i < p.NP; i++) {
-                uint64_t wv = p.wit[(size_t)i * N + r];
-                gl::e2 b = gl::add(gl::mul_base(p.beta, sigma[(size_t)i * N + r]), p.gamma);
-                b.c0 = gl::add(b.c0, wv);
-                d = gl::mul(d, b);
+                // w + gamma + beta*sigma as lazy residues (fused multiply-adds; the Ext2 multiply reduces once)
+                const uint64_t wg0 = gl::add(p.wit[(size_t)i * N + r], p.gamma.c0), sv = sigma[(size_t)i * N + r];
+                d = gl::mul(d, gl::make2(glx::fma(p.beta.c0, sv, wg0), glx::fma(p.beta.c1, sv, p.gamma.c1)));
             }
             suf = gl::mul(suf, d);
         }
@@ -190,10 +190,8 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
     uint64_t kx = x;
     for (uint32_t j = 0; j < p.C; j++) {
         for (uint32_t i = j * p.QD; i < (j + 1) * p.QD && i < p.NP; i++) {
-            uint64_t wv = p.wit[(size_t)i * N + r];
-            gl::e2 a = gl::add(gl::mul_base(p.beta, kx), p.gamma);
-            a.c0 = gl::add(a.c0, wv);
-            npre = gl::mul(npre, a);
+            const uint64_t wg0 = gl::add(p.wit[(size_t)i * N + r], p.gamma.c0);
+            npre = gl::mul(npre, gl::make2(glx::fma(p.beta.c0, kx, wg0), glx::fma(p.beta.c1, kx, p.gamma.c1)));
             kx = gl::mul(kx, GL_GEN);
         }
         gl::e2 q = gl::mul(gl::mul(npre, dsuf[j]), inv_all);

@@ -93,6 +93,9 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
         }
         __syncthreads();
     }
+    // Relation values are handed to the alpha dot product as LAZY residues (dot.cuh multiplies exact integers, any u64
+    // representative is fine): products are glx::mul / glx::fma (17 / 20 instructions, no canonicalisation), a canonical
+    // subtrahend is taken off with gl::sub, whose single borrow fix-up is exact for ANY minuend when the subtrahend is < p.
     const uint64_t* __restrict__ w = tile + lane;
     const uint64_t* __restrict__ kc = ktile + lane;
     const ulonglong2* __restrict__ apow = reinterpret_cast<const ulonglong2*>(p.apow);
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
 #pragma unroll 1
                 for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
-                    uint64_t r = gl::sub(gl::add(gl::mul(gl::mul(k0, x[0]), x[cw]), gl::mul(k1, x[2 * cw])), x[3 * cw]);
+                    uint64_t r = gl::sub(glx::fma(glx::mul(k0, x[0]), x[cw], glx::mul(k1, x[2 * cw])), x[3 * cw]);
                     dote_add(d, r, ap[t]);
                 }
             } break;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
 #pragma unroll 1
                 for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
-                    uint64_t s = gl::add(gl::add(gl::mul(k0, x[0]), gl::mul(k1, x[cw])), gl::add(gl::mul(k2, x[2 * cw]), gl::mul(k3, x[3 * cw])));
+                    uint64_t s = glx::fma(k3, x[3 * cw], glx::fma(k2, x[2 * cw], glx::fma(k1, x[cw], glx::mul(k0, x[0]))));
                     dote_add(d, gl::sub(s, x[4 * cw]), ap[t]);
                 }
             } break;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
                     uint64_t b = x[2 * cw];
                     // s*a + (1-s)*b - out = s*(a - b) + b - out
-                    dote_add(d, gl::sub(gl::add(gl::mul(x[0], gl::sub(x[cw], b)), b), x[3 * cw]), ap[t]);
+                    dote_add(d, gl::sub(glx::fma(x[0], gl::sub(x[cw], b), b), x[3 * cw]), ap[t]);
                 }
                 break;
             case ZKGPU_GATE_PARALLEL_SELECTION4:
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                     for (uint32_t i = 0; i < 4; i++) {
                         const uint64_t* y = x + (size_t)(1 + 3 * i) * cw;
                         uint64_t b = y[cw];
-                        dote_add(d, gl::sub(gl::add(gl::mul(s, gl::sub(y[0], b)), b), y[2 * cw]), ap[4 * t + i]);
+                        dote_add(d, gl::sub(glx::fma(s, gl::sub(y[0], b), b), y[2 * cw]), ap[4 * t + i]);
                     }
                 }
                 break;
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                 for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(3 * t) * cw;
                     uint64_t xv = x[0], zf = x[2 * cw];
-                    dote_add(d, gl::sub(gl::mul(xv, x[cw]), gl::sub(1, zf)), ap[2 * t]);
-                    dote_add(d, gl::mul(xv, zf), ap[2 * t + 1]);
+                    dote_add(d, gl::sub(glx::mul(xv, x[cw]), gl::sub(1, zf)), ap[2 * t]);
+                    dote_add(d, glx::mul(xv, zf), ap[2 * t + 1]);
                 }
                 break;
             case ZKGPU_GATE_UINTX_ADD: {
@@ -168,10 +171,11 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                 for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t co = x[4 * cw];
-                    uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
-                    uint64_t rhs = gl::add(x[3 * cw], gl::mul(k0, co));
-                    dote_add(d, gl::sub(lhs, rhs), ap[2 * t]);
-                    dote_add(d, gl::sub(gl::sqr(co), co), ap[2 * t + 1]);
+                    // a + b + cin - c - k*cout, as (a + b + cin) + (p - c) + k*(p - cout): every term canonical, sums lazy
+                    uint64_t lhs = glx::add_canon(glx::add_canon(x[0], x[cw]), x[2 * cw]);
+                    lhs = glx::add_canon(lhs, gl::neg(x[3 * cw]));
+                    dote_add(d, glx::fma(k0, gl::neg(co), lhs), ap[2 * t]);
+                    dote_add(d, gl::sub(glx::mul(co, co), co), ap[2 * t + 1]);
                 }
             } break;
             case ZKGPU_GATE_U32_TRI_ADD_CARRY:
@@ -240,8 +244,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
 #pragma unroll 1
                 for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
                     const uint64_t* x = w + (size_t)(9 * t) * cw;
-                    uint64_t s = gl::add(gl::add(gl::mul(x[0], x[cw]), gl::mul(x[2 * cw], x[3 * cw])),
-                                         gl::add(gl::mul(x[4 * cw], x[5 * cw]), gl::mul(x[6 * cw], x[7 * cw])));
+                    uint64_t s = glx::fma(x[6 * cw], x[7 * cw], glx::fma(x[4 * cw], x[5 * cw], glx::fma(x[2 * cw], x[3 * cw], glx::mul(x[0], x[cw]))));
                     dote_add(d, gl::sub(s, x[8 * cw]), ap[t]);
                 }
                 break;
@@ -373,7 +376,13 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ boolean, PI, lookup, copy permutation
-__device__ __forceinline__ uint64_t mul7(uint64_t x) { return gl::sub(glx::mul_2exp<3>(x), x); }
+// 7x for any u64 representative, lazy result: 8x - x as a 67-bit integer (never negative), one reduction
+__device__ __forceinline__ uint64_t mul7(uint64_t x) {
+    const uint64_t lo8 = x << 3;
+    const uint64_t lo = lo8 - x;
+    const uint32_t hi = (uint32_t)(x >> 61) - (lo8 < x ? 1u : 0u);
+    return glx::reduce96(lo, hi);
+}
 
 __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constant__ QuotParams p) {
     const uint32_t log_n = p.g.log_n;
@@ -448,11 +457,12 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
         const uint32_t i1 = min((c + 1) * QD, p.NP);
         ZK_UNROLL(ZK_PERM_UNROLL)
         for (uint32_t i = c * QD; i < i1; i++) {
-            const uint64_t wv = w[(size_t)i * cw];
-            gl::e2 a = gl::add(bkx, p.gamma);
-            a.c0 = gl::add(a.c0, wv);
-            gl::e2 b = gl::add(gl::mul_base(p.beta, sg[(size_t)i * cs]), p.gamma);
-            b.c0 = gl::add(b.c0, wv);
+            // the two linear forms as LAZY residues (the Ext2 multiply takes any u64 representative and reduces once):
+            // a = w + gamma + beta*k_i*x, b = w + gamma + beta*sigma_i with the additions folded into fused multiply-adds
+            const uint64_t wg0 = gl::add(w[(size_t)i * cw], p.gamma.c0);   // canonical: bkx below is lazy
+            const uint64_t sgv = sg[(size_t)i * cs];
+            gl::e2 a = gl::make2(glx::add_canon(bkx.c0, wg0), glx::add_canon(bkx.c1, p.gamma.c1));
+            gl::e2 b = gl::make2(glx::fma(p.beta.c0, sgv, wg0), glx::fma(p.beta.c1, sgv, p.gamma.c1));
             num = gl::mul(num, a);
             dn = gl::mul(dn, b);
             bkx = gl::make2(mul7(bkx.c0), mul7(bkx.c1));
