@@ -1,8 +1,8 @@
 """Poseidon2 pin against the reference's golden proofs -- hash-agnostic known answers (tools/make_hash_kat_fixture.py).
 
-These two tests are the mechanical definition of "Poseidon2 parity pinned" (DESIGN.md section 5): they are expected to FAIL
-while the restated parameters in oracle/primitives.c do not reproduce the digests in the golden proofs, and the strict xfail
-turns into a failure the day they do, so the marker (and the "parity unpinned" notes) must be removed together.
+These two tests are the mechanical definition of "Poseidon2 parity pinned" (DESIGN.md section 5).  They were strict xfails
+until the round-constant table was identified (tools/gen_poseidon_constants.py: the plonky2 table of the Crandall-prime era);
+they are hard gates now: the oracle's permutation, sponge framing and node hash reproduce the reference's digests.
 """
 import json, os
 import numpy as np
@@ -10,7 +10,6 @@ import pytest
 from tests import oracle_lib
 
 KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "poseidon2_kat.json")))
-UNPINNED = "Poseidon2 parameters of the un-vendored boojum crate: parity unpinned (DESIGN.md section 5)"
 
 
 def test_fixture_shape():
@@ -19,7 +18,6 @@ def test_fixture_shape():
     assert len(KAT["leaf"]["leaves"]) == 16 and all(len(l) == 8 for l in KAT["leaf"]["leaves"])
 
 
-@pytest.mark.xfail(reason=UNPINNED, strict=True)
 def test_node_hash_reproduces_golden_cap():
     """Some ordered pair of top-of-path siblings must hash to a cap entry (reference tree: boojum MerkleTreeWithCap)."""
     orc = oracle_lib.load()
@@ -29,7 +27,6 @@ def test_node_hash_reproduces_golden_cap():
     assert hits >= len(tops) // 2 - 1
 
 
-@pytest.mark.xfail(reason=UNPINNED, strict=True)
 def test_leaf_hash_reproduces_golden_cap():
     """Every leaf of the last FRI oracle (16 leaves, empty path) must hash to a cap entry."""
     orc = oracle_lib.load()
