@@ -60,13 +60,15 @@ void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
 
 constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;
 
-// boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, Poseidon2Goldilocks> [recalled; not observable without the hash]:
-// witnessed elements are buffered; a challenge request absorbs the buffer (rate 8, overwrite, zero padding, one permutation
-// per block) and the sponge's COMMITMENT -- the first 4 state lanes -- becomes the list of available challenges; when that list
-// runs out the state is permuted once more.  Query indexes come from a bit buffer (`BoolsBuffer`): every challenge contributes
-// its 64 - log2(LDE domain) low bits, LSB first, and an index takes log2(LDE domain) of them.
+// boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, Poseidon2Goldilocks>, PINNED on the reference's golden proofs
+// (tools/golden_transcript.py, tests/test_golden_transcript_cpu.py: z, the DEEP challenge and every FRI challenge equal the values
+// recovered hash-free, and every transcript-derived query index opens all Merkle paths of compression_1..4 and proof.json):
+// witnessed elements are buffered; a challenge request absorbs the buffer followed by a ONE (rate 8, overwrite, then zero fill,
+// one permutation per block; the state is never reset) and the 8 RATE lanes of the state become the list of available
+// challenges; when that list runs out the state is permuted once more.  Query indexes come from a bit buffer (`BoolsBuffer`):
+// every challenge contributes its 64 - log2(LDE domain) low bits, LSB first, and an index takes log2(LDE domain) of them.
 struct Transcript {
-    static constexpr int CHALLENGES_PER_PERMUTATION = 4;   // = capacity / digest width CW
+    static constexpr int CHALLENGES_PER_PERMUTATION = 8;   // the rate lanes
     uint64_t st[12] = {0};
     std::vector<uint64_t> buf;
     int pos = CHALLENGES_PER_PERMUTATION;
@@ -76,6 +78,7 @@ struct Transcript {
     void absorb(const gl::e2& e) { buf.push_back(e.c0); buf.push_back(e.c1); }
     uint64_t challenge() {
         if (!buf.empty()) {
+            buf.push_back(1);
             for (size_t i = 0; i < buf.size(); i += 8) {
                 for (size_t k = 0; k < 8; k++) st[k] = i + k < buf.size() ? buf[i + k] : 0;
                 host_poseidon2_permute(st);

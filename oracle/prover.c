@@ -121,11 +121,12 @@ EXPORT void orc_deep_at_point(const zkgpu_geometry *g, const uint64_t *wl, const
 }
 
 /* ------------------------------------------------------------------ transcript (Poseidon2 sponge, rate 8, overwrite)
- * boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, R> [recalled; not observable without the hash]: witnessed elements are
- * buffered; a challenge request absorbs the buffer (zero padding, one permutation per block of 8) and the sponge's commitment
- * -- the first TR_CHALLENGES = 4 lanes -- becomes the list of available challenges; when it runs out the state is permuted again.
- * Query indexes (`BoolsBuffer`): every challenge contributes its 64 - log2(LDE domain) low bits, LSB first. */
-#define TR_CHALLENGES 4
+ * boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, R>, pinned on the golden proofs (tools/golden_transcript.py): witnessed
+ * elements are buffered; a challenge request absorbs the buffer FOLLOWED BY A ONE (then zero fill, one permutation per block of
+ * 8, state never reset) and the TR_CHALLENGES = 8 rate lanes become the list of available challenges; when it runs out the
+ * state is permuted again.  Query indexes (`BoolsBuffer`): every challenge contributes its 64 - log2(LDE domain) low bits,
+ * LSB first. */
+#define TR_CHALLENGES 8
 typedef struct {
     uint64_t st[12];
     uint64_t *buf;
@@ -146,6 +147,8 @@ static void tr_absorb(tr_t *t, const uint64_t *v, size_t n) {
 }
 static uint64_t tr_challenge(tr_t *t) {
     if (t->len) {
+        const uint64_t one = 1;
+        tr_absorb(t, &one, 1);
         for (size_t i = 0; i < t->len; i += 8) {
             for (size_t k = 0; k < 8; k++) t->st[k] = i + k < t->len ? t->buf[i + k] : 0;
             orc_poseidon2_permute(t->st);
