@@ -44,6 +44,7 @@ SYMBOLS = {
     "zkgpu_setup_set_witness_maps": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p]),
     "zkgpu_prove_from_hints": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, sz, u64p, sz, u64p, u64p, sz]),
     "zkgpu_verify": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz]),
+    "zkgpu_verify_ex": (ci, [ctypes.c_void_p, ctypes.c_void_p, u64p, u64p, sz, ctypes.c_uint32]),
     "zkgpu_synth_trace": (ci, [ctypes.c_void_p, u64, u64p, u64p]),
     "zkgpu_synth_trace_instance": (ci, [ctypes.c_void_p, u64, u64, u64p, u64p]),
 }

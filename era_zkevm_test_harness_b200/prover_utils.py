@@ -196,12 +196,12 @@ def prove_from_variables(ctx, setup: SetupData, variable_values, multiplicities=
     return proof
 
 
-def verify_proof(geo: Geometry, cfg: ProofConfig, vk_cap, proof):
-    """-> (bool, message).  CPU only, like the reference verifier."""
+def verify_proof(geo: Geometry, cfg: ProofConfig, vk_cap, proof, skip_quotient_identity=False):
+    """-> (bool, message).  CPU only, like the reference verifier.  skip_quotient_identity: diagnostic (zkgpu_verify_ex)."""
     lib = _lib.load()
     vk_cap = np.ascontiguousarray(vk_cap, dtype=np.uint64)
     proof = np.ascontiguousarray(proof, dtype=np.uint64)
-    rc = lib.zkgpu_verify(ctypes.byref(geo), ctypes.byref(cfg), _p(vk_cap), _p(proof), proof.size)
+    rc = lib.zkgpu_verify_ex(ctypes.byref(geo), ctypes.byref(cfg), _p(vk_cap), _p(proof), proof.size, 1 if skip_quotient_identity else 0)
     if rc == 0:
         return True, ""
     msg = lib.zkgpu_last_error().decode()

@@ -212,6 +212,11 @@ ZKGPU_API int zkgpu_prove_from_hints(zkgpu_ctx* ctx, const zkgpu_setup* s, const
  * 1 if invalid (message says which check failed), >1 on malformed input. */
 ZKGPU_API int zkgpu_verify(const zkgpu_geometry* g, const zkgpu_proof_config* cfg, const uint64_t* vk_cap, const uint64_t* proof,
                            size_t proof_len_u64);
+/* Diagnostic form of zkgpu_verify: `flags` switches single checks off so the remaining ones can be run on proofs made by the
+ * reference itself (tools/golden_verify.py, tests/test_golden_verify_cpu.py).  flags = 0 is zkgpu_verify. */
+#define ZKGPU_VERIFY_SKIP_QUOTIENT_IDENTITY 1u
+ZKGPU_API int zkgpu_verify_ex(const zkgpu_geometry* g, const zkgpu_proof_config* cfg, const uint64_t* vk_cap, const uint64_t* proof,
+                              size_t proof_len_u64, uint32_t flags);
 
 /* Synthetic satisfying trace for a geometry (stands in for the reference's Rust synthesis, which cannot run in this
  * image): fills witness (W x n) and setup (S x n) columns deterministically from `seed`.  Host only. */

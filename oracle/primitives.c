@@ -240,6 +240,32 @@ EXPORT int orc_merkle_verify(const uint64_t *leaf_els, size_t leaf_len, const ui
     return memcmp(cur, cap + 4 * idx, 32) == 0;
 }
 
+/* Recovers the leaf index of a Merkle opening whose index is not stored (boojum's OracleQuery holds leaf + path only): all
+ * 2^path_len left/right patterns share prefixes, so the candidate roots cost 2^(path_len+1) node hashes; the pattern whose root
+ * is a cap entry gives idx = (cap position << path_len) | pattern.  Used by tools/golden_recover_vk_cap.py to rebuild the setup
+ * caps (= verification keys) the stale golden proofs were made with.  Returns the index or (size_t)-1. */
+EXPORT size_t orc_merkle_find_index(const uint64_t *leaf_els, size_t leaf_len, const uint64_t *path, size_t path_len, const uint64_t *cap,
+                                    size_t cap_size) {
+    size_t n = 1;
+    uint64_t *cur = (uint64_t *)malloc(32), *nxt;
+    orc_hash_leaf(leaf_els, leaf_len, cur);
+    for (size_t k = 0; k < path_len; k++) {   /* candidate j at level k -> 2j (we are the left child... bit k = 0) and 2j+1 */
+        nxt = (uint64_t *)malloc(64 * n);
+#pragma omp parallel for schedule(static)
+        for (size_t j = 0; j < n; j++) {
+            orc_hash_node(cur + 4 * j, path + 4 * k, nxt + 4 * j);            /* bit k of the index = 0 */
+            orc_hash_node(path + 4 * k, cur + 4 * j, nxt + 4 * (n + j));      /* bit k of the index = 1 */
+        }
+        free(cur); cur = nxt; n *= 2;                                          /* candidate c: its index bits are c's bits, bit k = c >> k & 1 */
+    }
+    size_t found = (size_t)-1;
+    for (size_t c = 0; c < n && found == (size_t)-1; c++)
+        for (size_t t = 0; t < cap_size; t++)
+            if (memcmp(cur + 4 * c, cap + 4 * t, 32) == 0) { found = (t << path_len) | c; break; }
+    free(cur);
+    return found;
+}
+
 /* ------------------------------------------------------------------ FRI folding */
 /* One un-normalised fold step of an Ext2 oracle stored split (c0[], c1[]) in bit-reversed enumeration.
  * Domain before the step: shift * <omega_{2^log_dom}>, point at index i = shift * omega^bitrev(i).

@@ -39,6 +39,7 @@ class Oracle:
         L.orc_merkle_build.argtypes = [vp, sz, sz, sz, sz, sz, vp]
         L.orc_merkle_path.argtypes = [vp, sz, sz, sz, vp]
         L.orc_merkle_verify.restype = ci; L.orc_merkle_verify.argtypes = [vp, sz, vp, sz, vp, sz]
+        L.orc_merkle_find_index.restype = sz; L.orc_merkle_find_index.argtypes = [vp, sz, vp, sz, vp, sz]
         L.orc_fri_fold.argtypes = [vp, vp, ci, c_u64, vp, vp, vp]
         L.orc_fri_fold_leaf.argtypes = [vp, vp, sz, ci, c_u64, sz, vp, vp]
         L.orc_eval_ext_poly_at_base.argtypes = [vp, vp, sz, c_u64, vp]
@@ -53,6 +54,7 @@ class Oracle:
             getattr(L, nm).restype = ctypes.c_uint32; getattr(L, nm).argtypes = [vp]
         L.orc_gl2_inv_vec.argtypes = [vp, vp, sz]
         L.orc_verify.restype = ci; L.orc_verify.argtypes = [vp, vp, vp, vp, sz, ctypes.c_char_p, sz]
+        L.orc_verify_ex.restype = ci; L.orc_verify_ex.argtypes = [vp, vp, vp, vp, sz, ctypes.c_uint, ctypes.c_char_p, sz]
         L.orc_set_threads.restype = ci; L.orc_set_threads.argtypes = [ci]
         L.orc_synth_trace.restype = ci; L.orc_synth_trace.argtypes = [vp, c_u64, c_u64, ci, vp, vp]
 
@@ -132,6 +134,13 @@ class Oracle:
         cap = np.ascontiguousarray(cap, dtype=np.uint64)
         return bool(self.lib.orc_merkle_verify(self._p(leaf), leaf.size, self._p(path), path.shape[0], self._p(cap), idx))
 
+    def merkle_find_index(self, leaf, path, cap):
+        """index of an opening whose index is not stored (oracle/primitives.c orc_merkle_find_index); None when no pattern fits"""
+        leaf = np.ascontiguousarray(leaf, dtype=np.uint64); path = np.ascontiguousarray(path, dtype=np.uint64).reshape(-1)
+        cap = np.ascontiguousarray(cap, dtype=np.uint64).reshape(-1)
+        r = self.lib.orc_merkle_find_index(self._p(leaf), leaf.size, self._p(path), path.size // 4, self._p(cap), cap.size // 4)
+        return None if r == (1 << 64) - 1 else int(r)
+
     def fri_fold(self, c0, c1, log_dom, shift, ch):
         c0 = np.ascontiguousarray(c0, dtype=np.uint64); c1 = np.ascontiguousarray(c1, dtype=np.uint64)
         half = 1 << (log_dom - 1)
@@ -167,11 +176,12 @@ class Oracle:
         assert w == n, (w, n)
         return proof
 
-    def verify(self, geo, cfg, vk_cap, proof):
+    def verify(self, geo, cfg, vk_cap, proof, skip_quotient_identity=False):
         """The oracle's own verifier (oracle/prover.c orc_verify), independent of the product's zkgpu_verify: (ok, message)."""
         cap = np.ascontiguousarray(vk_cap, dtype=np.uint64); pr = np.ascontiguousarray(proof, dtype=np.uint64)
         buf = ctypes.create_string_buffer(256)
-        rc = self.lib.orc_verify(ctypes.byref(geo), ctypes.byref(cfg), self._p(cap), self._p(pr), pr.size, buf, 256)
+        rc = self.lib.orc_verify_ex(ctypes.byref(geo), ctypes.byref(cfg), self._p(cap), self._p(pr), pr.size,
+                                    1 if skip_quotient_identity else 0, buf, 256)
         return rc == 0, buf.value.decode()
 
     def set_threads(self, n):

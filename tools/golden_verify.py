@@ -14,7 +14,9 @@ from era_zkevm_test_harness_b200 import geometry as G, proof_format as PF
 from tests import oracle_lib
 
 REF = "/root/reference"
-PAIRS = [("proof.json", "vk.json", "base_1")] + [(f"compression_{m}_proof.json", f"compression_{m}_vk.json", f"compression_{m}") for m in (1, 2, 3, 4)]
+PAIRS = ([("proof.json", "vk.json", "base_1")] + [(f"compression_{m}_proof.json", f"compression_{m}_vk.json", f"compression_{m}") for m in (1, 2, 3, 4)]
+         + [(f"test_proofs/base_layer/basic_circuit_proof_{t}_0.json", f"setup/base_layer/vk_{t}.json", f"base_{t}") for t in (4, 8, 13)]
+         + [(f"test_proofs/recursion_layer/node_layer_proof_{t}_0_0.json", "setup/recursion_layer/vk_node.json", "recursion") for t in range(3, 16)])
 
 
 def load_pair(proof_path, vk_path, kind):
@@ -39,7 +41,8 @@ def load_pair(proof_path, vk_path, kind):
 
 
 def main():
-    args = sys.argv[1:]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    skip = "--skip-quotient-identity" in sys.argv
     pairs = [(args[0], args[1], args[2])] if len(args) == 3 else [(os.path.join(REF, p), os.path.join(REF, v), k) for p, v, k in PAIRS]
     orc = oracle_lib.load()
     product = None
@@ -51,11 +54,11 @@ def main():
     rc = 0
     for p, v, k in pairs:
         geo, cfg, cap, flat = load_pair(p, v, k)
-        ok, msg = orc.verify(geo, cfg, cap, flat)
+        ok, msg = orc.verify(geo, cfg, cap, flat, skip_quotient_identity=skip)
         print(f"{os.path.basename(p):34s} oracle verifier: {'ACCEPT' if ok else 'reject: ' + msg}")
         rc |= not ok
         if product:
-            ok, msg = product.verify_proof(geo, cfg, cap, flat)
+            ok, msg = product.verify_proof(geo, cfg, cap, flat, skip_quotient_identity=skip)
             print(f"{'':34s} zkgpu_verify:    {'ACCEPT' if ok else 'reject: ' + msg}")
             rc |= not ok
     return rc
