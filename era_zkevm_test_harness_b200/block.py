@@ -124,9 +124,10 @@ def plan_block(base_instances: Dict[int, int], base_keys: Dict[int, str], leaf_k
 
 SYNTHETIC_NOTE = {
     "synthetic": True,
-    "why": "Artefacts of this directory are NOT interchangeable with the reference's files of the same names: (1) the Poseidon2 "
-           "parameters of the un-vendored boojum crate are unpinned (DESIGN.md section 5), so caps, challenges and query indexes "
-           "differ from boojum's; (2) witnesses and setup columns are synthetic satisfying traces of each circuit's geometry, and "
+    "why": "Artefacts of this directory are NOT interchangeable with the reference's files of the same names: (1) hashing, Merkle "
+           "trees, transcript, DEEP and FRI are pinned on the reference's golden proofs, but the gate polynomials / quotient term "
+           "order of the un-vendored boojum crate are not (DESIGN.md section 5), so the reference verifier would reject the quotient "
+           "identity; (2) witnesses and setup columns are synthetic satisfying traces of each circuit's geometry, and "
            "recursion / compression jobs do not verify their children in-circuit (the recursive-verifier synthesis is host Rust).",
 }
 

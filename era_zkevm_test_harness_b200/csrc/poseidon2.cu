@@ -1,8 +1,9 @@
 // poseidon2.cu -- Poseidon2-Goldilocks (width 12, rate 8, capacity 4, x^7, 4+22+4 rounds) sponge and Merkle tree with cap.
 //
 // Replaces `GoldilocksPoseidon2Sponge<AbsorptionModeOverwrite>` as tree hasher `H`
-// (/root/reference/src/prover_utils.rs:43) inside boojum's oracle commitment.  Parameters: see oracle/primitives.c
-// -- PARITY UNPINNED against the reference digests; bit-exact against the CPU oracle.
+// (/root/reference/src/prover_utils.rs:43) inside boojum's oracle commitment.  Parameters: see oracle/primitives.c and
+// tools/gen_poseidon_constants.py -- PINNED: the oracle's leaf and node hashes reproduce the digests of the reference's golden
+// proofs (tests/test_hash_pin_cpu.py, tests/test_golden_verify_cpu.py), and these kernels are bit-exact against the oracle.
 #include "zk_internal.cuh"
 #include "poseidon2_consts.cuh"
 #include "poseidon2_core.cuh"

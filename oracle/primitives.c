@@ -11,11 +11,10 @@
  * PARITY STATUS
  *   - field / extension / roots of unity / coset shift / bit-reversed LDE enumeration / un-normalised FRI fold with
  *     c, c^2, c^4: PINNED hash-free against golden proofs (tests/test_golden_fri.py on tests/golden fixtures).
- *   - Poseidon2 permutation and sponge framing: **PARITY UNPINNED**.  The parameters below are the recollected
- *     boojum parameters (round constants = plonky2 table, M4 external matrix, 2^s internal diagonal).  They do not
- *     reproduce the digests in the golden proofs (scratch searches over ~2.5e5 variants in
- *     this round found no match), so Merkle caps cannot be compared with the reference's.  The permutation is kept
- *     behind one table (poseidon2_consts.h + the two matrices here) so it can be swapped when pinned.
+ *   - Poseidon2 permutation, sponge framing, leaf / node hashing, Merkle caps: PINNED on the golden proofs.  Round constants =
+ *     the plonky2 table of the Crandall-prime era (tools/gen_poseidon_constants.py), M4 external matrix, 2^s internal
+ *     diagonal, zero-padded overwrite sponge: every Merkle path of every query of 21 golden (proof, VK) pairs verifies
+ *     (tests/test_hash_pin_cpu.py, tests/test_golden_verify_cpu.py, tools/golden_verify.py).
  */
 #include "gl64.h"
 #include "poseidon2_consts.h"

@@ -497,7 +497,7 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     /* ---- openings, in the order of the reference's `values_at_z`: variables + plain witness columns, constants, sigmas,
      * z + partial products, lookup multiplicities, lookup A polys + B, lookup table columns, quotient chunks.  The lookup-free
      * part (witness leaf, constants, sigmas, stage 2, quotient; setup leaf stored sigmas-then-constants) is pinned hash-free on
-     * golden proofs (tools/golden_deep.py, tests/golden/deep_*.json); the position of the lookup blocks is recalled. */
+     * golden proofs (tools/golden_deep.py, tests/golden/deep_*.json); the position of the lookup blocks was confirmed there too. */
     const uint32_t n_at_z = sh.n_at_z, n_at_0 = sh.n_at_0;
     open_src *src = (open_src *)malloc(sizeof(open_src) * n_at_z);
     if (opening_sources(g, src) != n_at_z) { fprintf(stderr, "oracle: opening count mismatch\n"); return -1; }

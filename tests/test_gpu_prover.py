@@ -196,7 +196,7 @@ def test_compute_setups_writes_reference_style_vk_files(gpu, oracle, tmp_path):
     fx = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vk_shapes.json")))
     paths = CS.generate_base_layer_vks(gpu, str(tmp_path), fx, log_n=9)
     paths.update(CS.generate_recursive_layer_vks(gpu, str(tmp_path), fx, log_n=9))
-    # the reference's file names, under <root>/synthetic/ with a manifest: synthetic setup columns + unpinned hash
+    # the reference's file names, under <root>/synthetic/ with a manifest: synthetic setup columns + unpinned gate polynomials
     assert os.path.exists(tmp_path / "synthetic" / "SYNTHETIC.json")
     assert sorted(os.listdir(tmp_path / "synthetic" / "base_layer")) == sorted(f"vk_{t}.json" for t in range(1, 14))
     assert sorted(os.listdir(tmp_path / "synthetic" / "recursion_layer")) == ["vk_1.json", "vk_3.json", "vk_node.json"]
