@@ -61,7 +61,8 @@ def eval_gate(name, c, v, k, n_consts, variant=0):
     elif name == "FmaBaseNoConst":
         for t in range(inst):
             x = v[4 * t:4 * t + 4]
-            out.append(esub(eadd(emul(emul(k[0], x[0]), x[1]), emul(k[1], x[2])), x[3]))
+            kq, kl = (k[1], k[0]) if alt & 1 else (k[0], k[1])
+            out.append(esub(eadd(emul(emul(kq, x[0]), x[1]), emul(kl, x[2])), x[3]))
     elif name == "Reduction4":
         for t in range(inst):
             x = v[5 * t:5 * t + 5]
@@ -69,20 +70,22 @@ def eval_gate(name, c, v, k, n_consts, variant=0):
     elif name == "Selection":
         for t in range(inst):
             x = v[4 * t:4 * t + 4]
-            if alt == 0: a, b, s, r = x          # boojum: a, b, selector, result
+            if alt & 1 == 0: a, b, s, r = x          # boojum: a, b, selector, result
             else: s, a, b, r = x
+            if alt & 2: a, b = b, a
             out.append(esub(eadd(emul(s, a), emul(esub(ONE, s), b)), r))
     elif name == "ParallelSelection4":
         for t in range(inst):
             x = v[13 * t:13 * t + 13]
-            if alt == 0:
+            if alt & 3 == 0:
                 s = x[0]; tri = [(x[1 + 3 * i], x[2 + 3 * i], x[3 + 3 * i]) for i in range(4)]
-            elif alt == 1:
+            elif alt & 3 == 1:
                 s = x[0]; tri = [(x[1 + i], x[5 + i], x[9 + i]) for i in range(4)]
-            elif alt == 2:
+            elif alt & 3 == 2:
                 s = x[12]; tri = [(x[3 * i], x[3 * i + 1], x[3 * i + 2]) for i in range(4)]
             else:
                 s = x[8]; tri = [(x[i], x[4 + i], x[9 + i]) for i in range(4)]
+            if alt & 4: tri = [(b, a, r) for a, b, r in tri]
             for a, b, r in tri: out.append(esub(eadd(emul(s, a), emul(esub(ONE, s), b)), r))
     elif name == "ZeroCheck":
         for t in range(inst):
