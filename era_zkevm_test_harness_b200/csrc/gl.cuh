@@ -19,8 +19,10 @@
 static __constant__ uint32_t gl_eps_opaque_c = 0xFFFFFFFFu;
 #define GL_EPS_OPAQUE gl_eps_opaque_c
 #define GL_HD __host__ __device__ __forceinline__
+#define GL_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define GL_HD inline
+#define GL_HD_NOINLINE static inline
 #endif
 
 namespace gl {
@@ -156,7 +158,28 @@ GL_HD uint64_t pow(uint64_t b, uint64_t e) {
     }
     return r;
 }
-GL_HD uint64_t inv(uint64_t a) { return pow(a, GL_P - 2); }
+// a^(2^n) * b
+GL_HD uint64_t sqr_n_mul(uint64_t a, int n, uint64_t b) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int i = 0; i < n; i++) a = sqr(a);
+    return mul(a, b);
+}
+// a^(p-2) by an addition chain: p - 2 = 2^64 - 2^32 - 1 = 2*((2^31 - 1)*2^32 + (2^31 - 1)) + 1 -- 63 squarings + 9 multiplications
+// instead of the 64 + 63 of square-and-multiply (the exponent has 63 one bits); the loops stay rolled (a fully unrolled inversion is
+// 40 KB of SASS per call site, and stage 2 / the quotient / the DEEP kernel each invert per row).  inv(0) = 0.
+GL_HD_NOINLINE uint64_t inv(uint64_t a) {
+    const uint64_t t2 = sqr_n_mul(a, 1, a);        // 2^2 - 1
+    const uint64_t t3 = sqr_n_mul(t2, 1, a);       // 2^3 - 1
+    const uint64_t t6 = sqr_n_mul(t3, 3, t3);      // 2^6 - 1
+    const uint64_t t12 = sqr_n_mul(t6, 6, t6);     // 2^12 - 1
+    const uint64_t t24 = sqr_n_mul(t12, 12, t12);  // 2^24 - 1
+    const uint64_t t30 = sqr_n_mul(t24, 6, t6);    // 2^30 - 1
+    const uint64_t t31 = sqr_n_mul(t30, 1, a);     // 2^31 - 1
+    const uint64_t t63 = sqr_n_mul(t31, 32, t31);  // (2^31 - 1) * 2^32 + 2^31 - 1
+    return sqr_n_mul(t63, 1, a);
+}
 GL_HD uint64_t omega(int log_n) {
     uint64_t w = GL_ROOT_2_32;
     for (int i = log_n; i < 32; i++) w = sqr(w);

@@ -174,13 +174,16 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
     gl::e2 inv_all;
     {
         gl::e2 suf = gl::make2(1, 0);
+#pragma unroll 1
         for (int j = (int)p.C - 1; j >= 0; j--) {
             dsuf[j] = suf;  // product of D_l for l > j
             gl::e2 d = gl::make2(1, 0);
+#pragma unroll 1
             for (uint32_t i = j * p.QD; i < (j + 1) * p.QD && i < p.NP; i++) {
                 // w + gamma + beta*sigma as lazy residues (fused multiply-adds; the Ext2 multiply reduces once)
                 const uint64_t wg0 = gl::add(p.wit[(size_t)i * N + r], p.gamma.c0), sv = sigma[(size_t)i * N + r];
-                d = gl::mul(d, gl::make2(glx::fma(p.beta.c0, sv, wg0), glx::fma(p.beta.c1, sv, p.gamma.c1)));
+                const gl::e2 f = gl::make2(glx::fma(p.beta.c0, sv, wg0), glx::fma(p.beta.c1, sv, p.gamma.c1));
+                if (i == j * p.QD) d = f; else d = gl::mul(d, f);   // no multiplication by one for the first column of a chunk
             }
             suf = gl::mul(suf, d);
         }
@@ -188,7 +191,9 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
     }
     gl::e2 npre = gl::make2(1, 0);
     uint64_t kx = x;
+#pragma unroll 1
     for (uint32_t j = 0; j < p.C; j++) {
+#pragma unroll 1
         for (uint32_t i = j * p.QD; i < (j + 1) * p.QD && i < p.NP; i++) {
             const uint64_t wg0 = gl::add(p.wit[(size_t)i * N + r], p.gamma.c0);
             npre = gl::mul(npre, gl::make2(glx::fma(p.beta.c0, kx, wg0), glx::fma(p.beta.c1, kx, p.gamma.c1)));
