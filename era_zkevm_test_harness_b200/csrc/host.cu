@@ -51,6 +51,7 @@ void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg) {
     ZK_REQUIRE(g.n_gates <= ZKGPU_MAX_GATES, "geometry: too many gates");
     ZK_REQUIRE(g.n_public_inputs <= ZKGPU_MAX_PUBLIC_INPUTS, "geometry: too many public inputs");
     ZK_REQUIRE((g.lookup_reps == 0) == (g.lookup_width == 0), "geometry: lookup width/reps inconsistent");
+    ZK_REQUIRE(g.lookup_reps <= 48, "geometry: more than 48 lookup repetitions (stage-2 per-row scratch)");
     ZK_REQUIRE(g.lookup_width <= 8, "geometry: lookup width > 8");
     ZK_REQUIRE(g.lookup_reps == 0 || g.table_id_col < g.n_const_cols, "geometry: table id column outside the constant columns");
     ZK_REQUIRE(g.table_len <= ((uint32_t)1 << g.log_n), "geometry: table longer than the trace");

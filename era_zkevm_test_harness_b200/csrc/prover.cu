@@ -148,6 +148,7 @@ static void extend_columns(Ctx* ctx, const uint64_t* vals, uint64_t* mono, uint6
 }
 
 // ------------------------------------------------------------------------------------------------ stage 2
+#define ZKGPU_MAX_LOOKUP_REPS 48   // per-row scratch of stage2_rows_kernel (validate(): lookup_reps <= 48; the reference's largest is 26)
 struct Stage2Params {
     const uint64_t* wit;     // [W][N]
     const uint64_t* setup;   // [S][N]
@@ -214,18 +215,38 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
         gp[0] = gl::make2(1, 0);
         for (uint32_t j = 1; j <= LW; j++) gp[j] = gl::mul(gp[j - 1], p.lgamma);
         gl::e2 tid = gl::mul_base(gp[LW], consts[(size_t)p.table_id_col * N + r]);
+        // all lookup_reps + 1 denominators are inverted together (Montgomery's trick: one field inversion and three Ext2
+        // multiplications per denominator instead of an inversion each)
+        gl::e2 den[ZKGPU_MAX_LOOKUP_REPS + 1], pre[ZKGPU_MAX_LOOKUP_REPS + 1];
+        const uint32_t nd = p.lookup_reps + 1;
+#pragma unroll 1
         for (uint32_t i = 0; i < p.lookup_reps; i++) {
-            gl::e2 den = gl::add(p.lbeta, tid);
-            for (uint32_t j = 0; j < LW; j++) den = gl::add(den, gl::mul_base(gp[j], p.wit[(size_t)(p.lookup_col0 + i * LW + j) * N + r]));
-            gl::e2 a = gl::inv(den);
-            p.s2[(size_t)(2 * (p.C + i)) * N + r] = a.c0;
-            p.s2[(size_t)(2 * (p.C + i) + 1) * N + r] = a.c1;
+            gl::e2 d = gl::add(p.lbeta, tid);
+            for (uint32_t j = 0; j < LW; j++) d = gl::add(d, gl::mul_base(gp[j], p.wit[(size_t)(p.lookup_col0 + i * LW + j) * N + r]));
+            den[i] = d;
         }
-        gl::e2 den = p.lbeta;
-        for (uint32_t j = 0; j <= LW; j++) den = gl::add(den, gl::mul_base(gp[j], tables[(size_t)j * N + r]));
-        gl::e2 b = gl::mul_base(gl::inv(den), p.wit[(size_t)(p.W - 1) * N + r]);
-        p.s2[(size_t)(2 * (p.C + p.lookup_reps)) * N + r] = b.c0;
-        p.s2[(size_t)(2 * (p.C + p.lookup_reps) + 1) * N + r] = b.c1;
+        {
+            gl::e2 d = p.lbeta;
+            for (uint32_t j = 0; j <= LW; j++) d = gl::add(d, gl::mul_base(gp[j], tables[(size_t)j * N + r]));
+            den[p.lookup_reps] = d;
+        }
+        gl::e2 run = gl::make2(1, 0);
+#pragma unroll 1
+        for (uint32_t i = 0; i < nd; i++) { pre[i] = run; run = gl::mul(run, den[i]); }
+        gl::e2 inv = gl::inv(run);   // a zero denominator (probability ~2^-120 per row) makes every inverse of the row zero, as inv(0) = 0 does
+#pragma unroll 1
+        for (uint32_t i = nd; i-- > 0;) {
+            const gl::e2 a = gl::mul(inv, pre[i]);   // 1 / den[i]
+            inv = gl::mul(inv, den[i]);
+            if (i < p.lookup_reps) {
+                p.s2[(size_t)(2 * (p.C + i)) * N + r] = a.c0;
+                p.s2[(size_t)(2 * (p.C + i) + 1) * N + r] = a.c1;
+            } else {
+                const gl::e2 b = gl::mul_base(a, p.wit[(size_t)(p.W - 1) * N + r]);
+                p.s2[(size_t)(2 * (p.C + p.lookup_reps)) * N + r] = b.c0;
+                p.s2[(size_t)(2 * (p.C + p.lookup_reps) + 1) * N + r] = b.c1;
+            }
+        }
     }
 }
 
