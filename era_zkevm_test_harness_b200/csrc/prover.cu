@@ -123,6 +123,33 @@ __global__ void omega_br_kernel(uint64_t* out, uint64_t omega, int log_n) {
     out[j] = gl::pow(omega, gl::bitrev((uint32_t)j, log_n));
 }
 
+// 1 / (n * (x - 1)) on every point of the quotient cosets, coset-major: the denominator of the Lagrange polynomial L_0 used by the
+// z(1) = 1 term.  Depends on the domain only, so it is computed once per context (one field inversion per point, 64 MB at 2^20 x 8)
+// instead of once per point and proof inside quotient_perm_kernel.
+__global__ void l0_inv_table_kernel(uint64_t* out, const uint64_t* omega_br, uint64_t shift, uint64_t n_field, size_t n) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    out[j] = gl::inv(gl::mul(n_field, gl::sub(gl::mul(shift, omega_br[j]), 1)));
+}
+static const uint64_t* get_omega_br(Ctx* ctx, int log_n);
+static const uint64_t* get_l0_inv_table(Ctx* ctx, int log_n, int log_qd) {
+    auto key = std::make_pair(-1000 - log_n, (uint64_t)log_qd);
+    auto it = ctx->coset_tables.find(key);
+    if (it != ctx->coset_tables.end()) return it->second.pre_e;
+    const size_t n = (size_t)1 << log_n, qd = (size_t)1 << log_qd;
+    const uint64_t* obr = get_omega_br(ctx, log_n);
+    uint64_t* d = (uint64_t*)ctx->alloc_persistent(n * qd * 8);
+    for (uint32_t c = 0; c < qd; c++) {
+        l0_inv_table_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d + (size_t)c * n, obr, lde_coset_shift(log_n, log_qd, c), (uint64_t)n % GL_P, n);
+        CUDA_CHECK(cudaGetLastError());
+        ctx->kernel_launches++;
+    }
+    CosetTables ct{};
+    ct.pre_e = d;
+    ctx->coset_tables.emplace(key, ct);
+    return d;
+}
+
 static const uint64_t* get_omega_br(Ctx* ctx, int log_n) {
     auto key = std::make_pair(-log_n - 1, (uint64_t)0);
     auto it = ctx->coset_tables.find(key);
@@ -613,6 +640,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.g = g;
         p.cs_w = (size_t)E * N; p.cs_s = (size_t)st.E * N; p.cs_2 = (size_t)E * N;
         p.omega_br = get_omega_br(ctx, log_n);
+        const uint64_t* l0_tab = get_l0_inv_table(ctx, log_n, log_qd);
         p.apow = d_apow.p; p.rc = d_rc.p;
         p.NP = sh.NP; p.C = sh.C; p.E2 = sh.E2; p.W = W; p.lookup_col0 = sh.lookup_col0;
         p.n_field = (uint64_t)N % GL_P;
@@ -639,6 +667,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
             p.shift = lde_coset_shift(log_n, log_qd, c);
             p.xn_minus_1 = gl::sub(gl::pow(p.shift, N), 1);
             p.zh_inv = gl::inv(p.xn_minus_1);
+            p.l0_inv = l0_tab + (size_t)c * N;
             p.t0 = tq.p + (size_t)c * N; p.t1 = tq.p + QN + (size_t)c * N;
             launch_quotient_coset(ctx, p);
         }

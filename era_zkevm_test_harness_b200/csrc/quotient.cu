@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
     }
     // 5a. Lagrange denominator N(x - 1) of L_0 (public inputs are not quotient terms: the reference opens them through the DEEP
     // polynomial, prover.cu deep_kernel)
-    const uint64_t l0_inv = gl::inv(gl::mul(p.n_field, gl::sub(x, 1)));
+    const uint64_t l0_inv = p.l0_inv[j];   // = 1 / (n (x - 1)), tabulated per context
     // 4. lookup
     if (g.lookup_reps) {
         const uint32_t LW = g.lookup_width;

@@ -11,6 +11,7 @@ struct QuotParams {
     const uint64_t* s2;     // stage-2 columns (c0, c1 interleaved per Ext2 polynomial)
     size_t cs_w, cs_s, cs_2;
     const uint64_t* omega_br;  // w^bitrev(j)
+    const uint64_t* l0_inv;    // 1 / (n (x_j - 1)) on this coset (prover.cu get_l0_inv_table)
     const uint64_t* apow;      // alpha^k, interleaved (c0, c1)
     const uint64_t* rc;        // Poseidon2 round constants (device copy)
     uint64_t* t0;
