@@ -158,16 +158,14 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t setup_seed, uint64_t s
     memset(consts, 0, (size_t)g.n_const_cols * N * 8);
     const uint64_t omega = gl::omega(g.log_n);
 
-    // identity permutation: sigma_i(w^r) = 7^i * w^r
+    // identity permutation: sigma_i(w^r) = k_i * w^r
+    const std::vector<uint64_t> knr = copy_permutation_non_residues(NP, (int)g.log_n);
     {
         std::vector<uint64_t> wp(N);
         uint64_t x = 1;
         for (size_t r = 0; r < N; r++) { wp[r] = x; x = gl::mul(x, omega); }
-        uint64_t k = 1;
-        for (uint32_t i = 0; i < NP; i++) {
-            for (size_t r = 0; r < N; r++) sigma[(size_t)i * N + r] = gl::mul(k, wp[r]);
-            k = gl::mul(k, GL_GEN);
-        }
+        for (uint32_t i = 0; i < NP; i++)
+            for (size_t r = 0; r < N; r++) sigma[(size_t)i * N + r] = gl::mul(knr[i], wp[r]);
     }
     // tables and multiplicities
     std::vector<uint64_t> mult;
@@ -202,7 +200,7 @@ static void synth_trace(const zkgpu_geometry& g, uint64_t setup_seed, uint64_t s
                         if (prev >= 0) {
                             // wire: input a of this row = output d of the previous FMA row (a 2-cycle in sigma)
                             x[0] = wit[(size_t)(4 * t + 3) * N + prev];
-                            uint64_t ka = gl::pow(GL_GEN, 4 * t), kd = gl::pow(GL_GEN, 4 * t + 3);
+                            uint64_t ka = knr[4 * t], kd = knr[4 * t + 3];
                             sigma[(size_t)(4 * t) * N + r] = gl::mul(kd, gl::pow(omega, (uint64_t)prev));
                             sigma[(size_t)(4 * t + 3) * N + prev] = gl::mul(ka, gl::pow(omega, r));
                         }
@@ -497,13 +495,13 @@ static void verify(const zkgpu_geometry& g, const zkgpu_proof_config& cfg, const
             gl::e2 l0 = gl::mul(zh, gl::inv(gl::mul_base(gl::sub(z, one), n_field)));
             acc = gl::add(acc, gl::mul(ap, gl::mul(l0, gl::sub(e2v[0], one))));
             ap = gl::mul(ap, alpha);
-            gl::e2 kx = z;
+            const std::vector<uint64_t> knr = copy_permutation_non_residues(sh.NP, (int)g.log_n);
             for (uint32_t j = 0; j < sh.C; j++) {
                 gl::e2 num = one, den = one;
                 for (uint32_t i = j * sh.QD; i < (j + 1) * sh.QD && i < sh.NP; i++) {
+                    const gl::e2 kx = gl::mul_base(z, knr[i]);
                     num = gl::mul(num, gl::add(gl::add(w[i], gl::mul(beta, kx)), gamma));
                     den = gl::mul(den, gl::add(gl::add(w[i], gl::mul(beta, sigma[i])), gamma));
-                    kx = gl::mul_base(kx, GL_GEN);
                 }
                 gl::e2 cur = (j + 1 < sh.C) ? e2v[j + 1] : at_zw;
                 acc = gl::add(acc, gl::mul(ap, gl::sub(gl::mul(cur, den), gl::mul(e2v[j], num))));

@@ -58,6 +58,27 @@ inline std::vector<uint32_t> opening_positions(const zkgpu_geometry& g, const Sh
 }
 void validate(const zkgpu_geometry& g, const zkgpu_proof_config& cfg);
 
+// Copy-permutation non-residues k_0 .. k_{n-1} (column i of the permutation argument lives on the coset k_i * H).  boojum's
+// `non_residues_for_copy_permutation` -> `make_non_residues` (the bellman routine): k_0 = 1, then the successive smallest quadratic
+// non-residues whose cosets are new: 7, 11, 13, 14, 19, 21, 22 ... [recalled; the sigma columns the Rust side hands over are built
+// with boojum's values, so this table has to equal them -- not observable on the golden proofs until the quotient identity is
+// pinned, DESIGN.md section 5].
+inline std::vector<uint64_t> copy_permutation_non_residues(uint32_t n, int log_n) {
+    std::vector<uint64_t> k, seen;
+    if (n == 0) return k;
+    k.push_back(1); seen.push_back(1);
+    for (uint64_t cur = 2; k.size() < n; cur++) {
+        if (gl::pow(cur, (GL_P - 1) / 2) != GL_P - 1) continue;   // a square
+        uint64_t t = cur;
+        for (int i = 0; i < log_n; i++) t = gl::sqr(t);            // cur^(domain size) decides the coset
+        bool dup = false;
+        for (uint64_t s : seen) dup |= s == t;
+        if (dup) continue;
+        k.push_back(cur); seen.push_back(t);
+    }
+    return k;
+}
+
 constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;
 
 // boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, Poseidon2Goldilocks>, PINNED on the reference's golden proofs

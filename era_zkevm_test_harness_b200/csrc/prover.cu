@@ -132,6 +132,22 @@ __global__ void l0_inv_table_kernel(uint64_t* out, const uint64_t* omega_br, uin
     out[j] = gl::inv(gl::mul(n_field, gl::sub(gl::mul(shift, omega_br[j]), 1)));
 }
 static const uint64_t* get_omega_br(Ctx* ctx, int log_n);
+static void h2d(Ctx* ctx, void* dst, const void* src, size_t bytes);
+// copy-permutation non-residues on the device (512 entries per trace length, uploaded once per context)
+static const uint64_t* get_non_residues(Ctx* ctx, uint32_t n, int log_n) {
+    ZK_REQUIRE(n <= 512, "prove: more than 512 copy-permuted columns");
+    auto key = std::make_pair(-2000 - log_n, (uint64_t)0);
+    auto it = ctx->coset_tables.find(key);
+    if (it != ctx->coset_tables.end()) return it->second.pre_e;
+    const std::vector<uint64_t> k = copy_permutation_non_residues(512, log_n);
+    uint64_t* d = (uint64_t*)ctx->alloc_persistent(512 * 8);
+    h2d(ctx, d, k.data(), 512 * 8);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // k is a stack-lifetime host vector
+    CosetTables ct{};
+    ct.pre_e = d;
+    ctx->coset_tables.emplace(key, ct);
+    return d;
+}
 static const uint64_t* get_l0_inv_table(Ctx* ctx, int log_n, int log_qd) {
     auto key = std::make_pair(-1000 - log_n, (uint64_t)log_qd);
     auto it = ctx->coset_tables.find(key);
@@ -181,6 +197,7 @@ struct Stage2Params {
     const uint64_t* setup;   // [S][N]
     uint64_t* s2;            // [S2][N]
     uint64_t* rowprod;       // [2][N]  (c0 | c1)
+    const uint64_t* knr;     // [NP] copy-permutation non-residues k_i (host_common.cuh)
     uint32_t log_n, NP, C, QD, W, n_const_cols, lookup_width, lookup_reps, table_id_col, lookup_col0;
     gl::e2 beta, gamma, lbeta, lgamma;
     uint64_t omega;
@@ -218,14 +235,13 @@ __global__ void __launch_bounds__(128) stage2_rows_kernel(Stage2Params p) {
         inv_all = gl::inv(suf);
     }
     gl::e2 npre = gl::make2(1, 0);
-    uint64_t kx = x;
 #pragma unroll 1
     for (uint32_t j = 0; j < p.C; j++) {
 #pragma unroll 1
         for (uint32_t i = j * p.QD; i < (j + 1) * p.QD && i < p.NP; i++) {
             const uint64_t wg0 = gl::add(p.wit[(size_t)i * N + r], p.gamma.c0);
+            const uint64_t kx = gl::mul(p.knr[i], x);   // k_i * x
             npre = gl::mul(npre, gl::make2(glx::fma(p.beta.c0, kx, wg0), glx::fma(p.beta.c1, kx, p.gamma.c1)));
-            kx = gl::mul(kx, GL_GEN);
         }
         gl::e2 q = gl::mul(gl::mul(npre, dsuf[j]), inv_all);
         if (j + 1 < p.C) {
@@ -612,6 +628,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.log_n = g.log_n; p.NP = sh.NP; p.C = sh.C; p.QD = QD; p.W = W; p.n_const_cols = g.n_const_cols;
         p.lookup_width = g.lookup_width; p.lookup_reps = g.lookup_reps; p.table_id_col = g.table_id_col; p.lookup_col0 = sh.lookup_col0;
         p.beta = beta; p.gamma = gamma; p.lbeta = lbeta; p.lgamma = lgamma; p.omega = gl::omega(log_n);
+        p.knr = get_non_residues(ctx, sh.NP, log_n);
         ZK_REQUIRE(sh.C <= 40, "prove: too many copy-permutation chunks");
         stage2_rows_kernel<<<(unsigned)((N + 127) / 128), 128, 0, stream>>>(p);
         LAUNCH_CHECK(ctx);
@@ -631,6 +648,12 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         std::vector<uint64_t> apow(2 * (size_t)sh.n_terms);
         gl::e2 a = gl::make2(1, 0);
         for (uint32_t i = 0; i < sh.n_terms; i++) { apow[2 * i] = a.c0; apow[2 * i + 1] = a.c1; a = gl::mul(a, alpha); }
+        // beta * k_i per copy-permuted column (Ext2, interleaved), behind the alpha powers in the same upload
+        const size_t bk_off = apow.size();
+        {
+            const std::vector<uint64_t> knr = copy_permutation_non_residues(sh.NP, log_n);
+            for (uint32_t i = 0; i < sh.NP; i++) { const gl::e2 bk = gl::mul_base(beta, knr[i]); apow.push_back(bk.c0); apow.push_back(bk.c1); }
+        }
         d_apow.alloc(apow.size(), stream);
         h2d(ctx, d_apow.p, apow.data(), apow.size() * 8);
         d_rc.alloc(360, stream);
@@ -641,7 +664,7 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
         p.cs_w = (size_t)E * N; p.cs_s = (size_t)st.E * N; p.cs_2 = (size_t)E * N;
         p.omega_br = get_omega_br(ctx, log_n);
         const uint64_t* l0_tab = get_l0_inv_table(ctx, log_n, log_qd);
-        p.apow = d_apow.p; p.rc = d_rc.p;
+        p.apow = d_apow.p; p.rc = d_rc.p; p.beta_k = d_apow.p + bk_off;
         p.NP = sh.NP; p.C = sh.C; p.E2 = sh.E2; p.W = W; p.lookup_col0 = sh.lookup_col0;
         p.n_field = (uint64_t)N % GL_P;
         p.beta = beta; p.gamma = gamma; p.lbeta = lbeta; p.lgamma = lgamma;

@@ -376,14 +376,6 @@ __global__ void __launch_bounds__(128) quotient_p2_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ boolean, PI, lookup, copy permutation
-// 7x for any u64 representative, lazy result: 8x - x as a 67-bit integer (never negative), one reduction
-__device__ __forceinline__ uint64_t mul7(uint64_t x) {
-    const uint64_t lo8 = x << 3;
-    const uint64_t lo = lo8 - x;
-    const uint32_t hi = (uint32_t)(x >> 61) - (lo8 < x ? 1u : 0u);
-    return glx::reduce96(lo, hi);
-}
-
 __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constant__ QuotParams p) {
     const uint32_t log_n = p.g.log_n;
     const size_t N = (size_t)1 << log_n;
@@ -447,8 +439,8 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
     const uint32_t nat = gl::bitrev((uint32_t)j, log_n);
     const size_t jn = gl::bitrev((nat + 1) & (uint32_t)(N - 1), log_n);
     const gl::e2 zs = gl::make2(p.s2[jn], p.s2[c2 + jn]);
-    // a_i = w_i + beta*k_i*x + gamma with k_i = 7^i: keep u = beta*k_i*x + gamma - gamma and step it by a multiply-by-7
-    gl::e2 bkx = gl::mul_base(p.beta, x);
+    // a_i = w_i + gamma + (beta*k_i)*x with beta*k_i from the per-proof table (k_i = copy-permutation non-residues)
+    const ulonglong2* __restrict__ bkt = reinterpret_cast<const ulonglong2*>(p.beta_k);
     gl::e2 prev = zv;
     const uint32_t QD = g.quotient_degree;
     // one flat loop over the copy-permuted columns with the loads of column i+1 issued before the arithmetic of column i (ncu: the
@@ -463,8 +455,9 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
         const uint64_t wn = w[(size_t)in * cw], sgn = sg[(size_t)in * cs];
         // the two linear forms as LAZY residues (the Ext2 multiply takes any u64 representative and reduces once):
         // a = w + gamma + beta*k_i*x, b = w + gamma + beta*sigma_i with the additions folded into fused multiply-adds
-        const uint64_t wg0 = gl::add(wv, p.gamma.c0);   // canonical: bkx below is lazy
-        gl::e2 a = gl::make2(glx::add_canon(bkx.c0, wg0), glx::add_canon(bkx.c1, p.gamma.c1));
+        const uint64_t wg0 = gl::add(wv, p.gamma.c0);
+        const ulonglong2 bk = bkt[i];
+        gl::e2 a = gl::make2(glx::fma(bk.x, x, wg0), glx::fma(bk.y, x, p.gamma.c1));
         gl::e2 b = gl::make2(glx::fma(p.beta.c0, sgv, wg0), glx::fma(p.beta.c1, sgv, p.gamma.c1));
         if (first) {   // first column of a chunk: no multiplication by one (uniform branch: every thread is at the same column)
             num = a; dn = b; first = false;   // lazy residues are fine: the Ext2 multiply takes any u64 representative
@@ -472,7 +465,6 @@ __global__ void __launch_bounds__(128) quotient_perm_kernel(const __grid_constan
             num = gl::mul(num, a);
             dn = gl::mul(dn, b);
         }
-        bkx = gl::make2(mul7(bkx.c0), mul7(bkx.c1));
         wv = wn; sgv = sgn;
         if (--left == 0) {   // end of chunk c
             gl::e2 cur = (c + 1 < p.C) ? gl::make2(e2[(size_t)(2 * (c + 1)) * c2], e2[(size_t)(2 * (c + 1) + 1) * c2]) : zs;

@@ -13,6 +13,7 @@ struct QuotParams {
     const uint64_t* omega_br;  // w^bitrev(j)
     const uint64_t* l0_inv;    // 1 / (n (x_j - 1)) on this coset (prover.cu get_l0_inv_table)
     const uint64_t* apow;      // alpha^k, interleaved (c0, c1)
+    const uint64_t* beta_k;    // beta * k_i for every copy-permuted column, interleaved (c0, c1); k_i = copy-permutation non-residues
     const uint64_t* rc;        // Poseidon2 round constants (device copy)
     uint64_t* t0;
     uint64_t* t1;              // output (split Ext2), offset to the coset

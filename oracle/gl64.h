@@ -96,4 +96,26 @@ static inline uint32_t bitrev32(uint32_t x, int bits) {
     for (int i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
     return r;
 }
+
+/* Copy-permutation non-residues k_0 .. k_{n-1}: column i of the permutation argument lives on the coset k_i * H.  boojum
+ * (`non_residues_for_copy_permutation` -> `make_non_residues`, the bellman routine): k_0 = 1, then the successive smallest
+ * quadratic non-residues whose cosets k * H are new -- 7, 11, 13, 14, 19, 21, 22, ... in Goldilocks for every domain size used
+ * here [recalled; not observable on the golden proofs until the quotient identity is pinned, DESIGN.md section 5]. */
+static inline void gl_copy_permutation_non_residues(uint64_t *k, uint32_t n, int log_n) {
+    uint64_t cur = 1;
+    uint32_t have = 0;
+    uint64_t seen[1024];
+    if (n == 0) return;
+    k[have] = 1; seen[have++] = 1;
+    while (have < n && have < 1024) {
+        cur++;
+        if (gl_pow(cur, (GL_P - 1) / 2) != GL_P - 1) continue;         /* a square */
+        uint64_t t = cur;
+        for (int i = 0; i < log_n; i++) t = gl_sqr(t);                  /* cur^(domain size) decides the coset */
+        int dup = 0;
+        for (uint32_t j = 0; j < have; j++) dup |= seen[j] == t;
+        if (dup) continue;
+        k[have] = cur; seen[have++] = t;
+    }
+}
 #endif

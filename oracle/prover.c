@@ -251,6 +251,7 @@ typedef struct {
     gl2 *alpha_pow;     /* alpha^k for every term */
     uint32_t n_terms;
     uint64_t *pi_values; /* public input values */
+    uint64_t knr[1024];  /* copy-permutation non-residues k_i (gl64.h gl_copy_permutation_non_residues) */
 } chal_t;
 
 static uint32_t count_terms(const zkgpu_geometry *g) {
@@ -319,17 +320,16 @@ static gl2 quotient_numerator(const zkgpu_geometry *g, const chal_t *ch, const u
         uint64_t l0 = gl_mul(xn_minus_1, gl_inv(gl_mul(N % GL_P, gl_sub(x, 1))));
         gl2 t = gl2_mul_base(gl2_sub(e2[0], gl2_make(1, 0)), l0);
         acc = gl2_add(acc, gl2_mul(ch->alpha_pow[k++], t));
-        uint64_t kx = x; /* k_i * x, k_i = 7^i */
         for (uint32_t j = 0; j < C; j++) {
             gl2 num = gl2_make(1, 0), den = gl2_make(1, 0);
             for (uint32_t i = j * QD; i < (j + 1) * QD && i < NP; i++) {
+                const uint64_t kx = gl_mul(ch->knr[i], x); /* k_i * x */
                 gl2 a = gl2_add(gl2_mul_base(ch->beta, kx), ch->gamma);
                 a.c0 = gl_add(a.c0, w[i]);
                 gl2 b = gl2_add(gl2_mul_base(ch->beta, sigma[i]), ch->gamma);
                 b.c0 = gl_add(b.c0, w[i]);
                 num = gl2_mul(num, a);
                 den = gl2_mul(den, b);
-                kx = gl_mul(kx, GL_GEN);
             }
             gl2 prev = e2[j]; /* j = 0: z, else p_{j-1} */
             gl2 cur = (j + 1 < C) ? e2[j + 1] : zs;
@@ -366,6 +366,7 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
     tr_absorb(&tr, pi_values, g->n_public_inputs);
     tr_absorb(&tr, tree_w + cap_off, cap * 4);
     chal_t ch; memset(&ch, 0, sizeof(ch));
+    gl_copy_permutation_non_residues(ch.knr, n_perm(g), (int)g->log_n);
     ch.beta = tr_challenge_ext(&tr);
     ch.gamma = tr_challenge_ext(&tr);
     if (g->lookup_reps) { ch.lbeta = tr_challenge_ext(&tr); ch.lgamma = tr_challenge_ext(&tr); }
@@ -380,15 +381,14 @@ EXPORT long orc_prove(const zkgpu_geometry *g, const zkgpu_proof_config *cfg, co
         gl2 *nums = (gl2 *)malloc(sizeof(gl2) * C), *dens = (gl2 *)malloc(sizeof(gl2) * C);
         for (size_t r = 0; r < N; r++) {
             s2[0 * N + r] = z.c0; s2[1 * N + r] = z.c1;
-            uint64_t kx = x;
             for (uint32_t j = 0; j < C; j++) {
                 gl2 num = gl2_make(1, 0), den = gl2_make(1, 0);
                 for (uint32_t i = j * QD; i < (j + 1) * QD && i < NP; i++) {
                     uint64_t wv = wit_cols[(size_t)i * N + r];
+                    const uint64_t kx = gl_mul(ch.knr[i], x);
                     gl2 a = gl2_add(gl2_mul_base(ch.beta, kx), ch.gamma); a.c0 = gl_add(a.c0, wv);
                     gl2 b = gl2_add(gl2_mul_base(ch.beta, sigma[(size_t)i * N + r]), ch.gamma); b.c0 = gl_add(b.c0, wv);
                     num = gl2_mul(num, a); den = gl2_mul(den, b);
-                    kx = gl_mul(kx, GL_GEN);
                 }
                 nums[j] = num; dens[j] = den;
             }
@@ -685,6 +685,7 @@ EXPORT int orc_verify_ex(const zkgpu_geometry *g, const zkgpu_proof_config *cfg,
     const uint64_t omega = gl_omega(log_n);
     open_src *src = NULL; gl2 *wz = NULL, *sz = NULL, *ez = NULL, *qz = NULL, *phip = NULL; uint64_t *scratch = NULL, *cells = NULL;
     chal_t ch; memset(&ch, 0, sizeof(ch));
+    gl_copy_permutation_non_residues(ch.knr, n_perm(g), (int)g->log_n);
     tr_t tr; tr_init(&tr);
     uint64_t *canon_copy = NULL;
     if (msg_len) msg[0] = 0;
@@ -818,13 +819,12 @@ EXPORT int orc_verify_ex(const zkgpu_geometry *g, const zkgpu_proof_config *cfg,
         {
             const gl2 l0 = gl2_mul(zn_minus_1, gl2_inv(gl2_mul_base(gl2_sub(z, gl2_make(1, 0)), (uint64_t)N % GL_P)));
             acc = gl2_add(acc, gl2_mul(ap[k++], gl2_mul(gl2_sub(ez[0], gl2_make(1, 0)), l0)));
-            gl2 kx = z;
             for (uint32_t j = 0; j < C; j++) {
                 gl2 num = gl2_make(1, 0), den = gl2_make(1, 0);
                 for (uint32_t i = j * QD; i < (j + 1) * QD && i < NP; i++) {
+                    const gl2 kx = gl2_mul_base(z, ch.knr[i]);
                     num = gl2_mul(num, gl2_add(gl2_add(gl2_mul(ch.beta, kx), ch.gamma), wz[i]));
                     den = gl2_mul(den, gl2_add(gl2_add(gl2_mul(ch.beta, sigma[i]), ch.gamma), wz[i]));
-                    kx = gl2_mul_base(kx, GL_GEN);
                 }
                 const gl2 cur = (j + 1 < C) ? ez[j + 1] : at_zw;
                 acc = gl2_add(acc, gl2_mul(ap[k++], gl2_sub(gl2_mul(cur, den), gl2_mul(ez[j], num))));

@@ -44,13 +44,13 @@ EXPORT int orc_synth_trace(const zkgpu_geometry *g, uint64_t setup_seed, uint64_
     memset(consts, 0, (size_t)g->n_const_cols * N * 8);
     const uint64_t omega = gl_omega((int)g->log_n);
 
-    { /* identity permutation: sigma_i(w^r) = 7^i * w^r */
-        uint64_t *wp = (uint64_t *)malloc(N * 8), x = 1, k = 1;
+    uint64_t knr[1024]; /* copy-permutation non-residues k_i (gl64.h) */
+    gl_copy_permutation_non_residues(knr, NP, (int)g->log_n);
+    { /* identity permutation: sigma_i(w^r) = k_i * w^r */
+        uint64_t *wp = (uint64_t *)malloc(N * 8), x = 1;
         for (size_t r = 0; r < N; r++) { wp[r] = x; x = gl_mul(x, omega); }
-        for (uint32_t i = 0; i < NP; i++) {
-            for (size_t r = 0; r < N; r++) sigma[(size_t)i * N + r] = gl_mul(k, wp[r]);
-            k = gl_mul(k, GL_GEN);
-        }
+        for (uint32_t i = 0; i < NP; i++)
+            for (size_t r = 0; r < N; r++) sigma[(size_t)i * N + r] = gl_mul(knr[i], wp[r]);
         free(wp);
     }
     uint64_t *mult = NULL;
@@ -83,7 +83,7 @@ EXPORT int orc_synth_trace(const zkgpu_geometry *g, uint64_t setup_seed, uint64_
                     uint64_t *x = v + 4 * t;
                     if (prev >= 0) { /* wire: input a of this row = output d of the previous FMA row (a 2-cycle in sigma) */
                         x[0] = wit[(size_t)(4 * t + 3) * N + prev];
-                        const uint64_t ka = gl_pow(GL_GEN, 4 * t), kd = gl_pow(GL_GEN, 4 * t + 3);
+                        const uint64_t ka = knr[4 * t], kd = knr[4 * t + 3];
                         sigma[(size_t)(4 * t) * N + r] = gl_mul(kd, gl_pow(omega, (uint64_t)prev));
                         sigma[(size_t)(4 * t + 3) * N + prev] = gl_mul(ka, gl_pow(omega, r));
                     }
