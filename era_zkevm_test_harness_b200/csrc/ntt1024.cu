@@ -206,7 +206,10 @@ static const Ntt1024Tables::Coset& coset_tables(Ctx* ctx, uint64_t shift) {
 
 template <bool A, bool B, bool C, bool D>
 static void launch(Ctx* ctx, const Ntt1024Params& p, int n_polys) {
-    constexpr size_t smem = (size_t)(1024 + 32 + NT_T * NT_SP) * sizeof(uint64_t);
+#ifndef ZK_NTT_SMEM_PAD
+#define ZK_NTT_SMEM_PAD 0   // occupancy experiments: extra dynamic shared memory per CTA
+#endif
+    constexpr size_t smem = (size_t)(1024 + 32 + NT_T * NT_SP) * sizeof(uint64_t) + ZK_NTT_SMEM_PAD;
     static bool attr_set[64] = {};   // the attribute is per device: one process may hold contexts on several GPUs
     if (!attr_set[ctx->device & 63]) {
         CUDA_CHECK(cudaFuncSetAttribute(ntt1024_kernel<A, B, C, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
