@@ -265,6 +265,9 @@ EXPORT size_t orc_merkle_find_index(const uint64_t *leaf_els, size_t leaf_len, c
     return found;
 }
 
+/* the copy-permutation non-residue table of gl64.h, exported for the CPU suite */
+EXPORT void orc_copy_permutation_non_residues(uint64_t *k, uint32_t n, int log_n) { gl_copy_permutation_non_residues(k, n, log_n); }
+
 /* ------------------------------------------------------------------ FRI folding */
 /* One un-normalised fold step of an Ext2 oracle stored split (c0[], c1[]) in bit-reversed enumeration.
  * Domain before the step: shift * <omega_{2^log_dom}>, point at index i = shift * omega^bitrev(i).

@@ -40,6 +40,7 @@ class Oracle:
         L.orc_merkle_path.argtypes = [vp, sz, sz, sz, vp]
         L.orc_merkle_verify.restype = ci; L.orc_merkle_verify.argtypes = [vp, sz, vp, sz, vp, sz]
         L.orc_merkle_find_index.restype = sz; L.orc_merkle_find_index.argtypes = [vp, sz, vp, sz, vp, sz]
+        L.orc_copy_permutation_non_residues.argtypes = [vp, ctypes.c_uint32, ci]
         L.orc_fri_fold.argtypes = [vp, vp, ci, c_u64, vp, vp, vp]
         L.orc_fri_fold_leaf.argtypes = [vp, vp, sz, ci, c_u64, sz, vp, vp]
         L.orc_eval_ext_poly_at_base.argtypes = [vp, vp, sz, c_u64, vp]
@@ -140,6 +141,11 @@ class Oracle:
         cap = np.ascontiguousarray(cap, dtype=np.uint64).reshape(-1)
         r = self.lib.orc_merkle_find_index(self._p(leaf), leaf.size, self._p(path), path.size // 4, self._p(cap), cap.size // 4)
         return None if r == (1 << 64) - 1 else int(r)
+
+    def copy_permutation_non_residues(self, n, log_n):
+        k = np.zeros(n, dtype=np.uint64)
+        self.lib.orc_copy_permutation_non_residues(self._p(k), n, log_n)
+        return k
 
     def fri_fold(self, c0, c1, log_dom, shift, ch):
         c0 = np.ascontiguousarray(c0, dtype=np.uint64); c1 = np.ascontiguousarray(c1, dtype=np.uint64)

@@ -224,3 +224,15 @@ def test_golden_lookup_sum_check_at_zero():
         s0 = sum(v[0] for v in vals[:-1]) % P
         s1 = sum(v[1] for v in vals[:-1]) % P
         assert [s0, s1] == vals[-1], name
+
+
+def test_copy_permutation_non_residues(oracle):
+    """k_0 = 1, then the successive quadratic non-residues whose cosets k * H are new (boojum make_non_residues, recalled):
+    the list is the same for every trace length used here, every k_i (i > 0) is a non-residue and the cosets are disjoint."""
+    P = (1 << 64) - (1 << 32) + 1
+    want = [1, 7, 11, 13, 14, 19, 21, 22, 26, 28, 31, 33, 35, 37, 38, 39, 42, 43, 44, 47]
+    for log_n in (8, 16, 20):
+        k = [int(x) for x in oracle.copy_permutation_non_residues(200, log_n)]
+        assert k[:20] == want
+        assert all(pow(x, (P - 1) // 2, P) == P - 1 for x in k[1:])
+        assert len({pow(x, 1 << log_n, P) for x in k}) == len(k)
