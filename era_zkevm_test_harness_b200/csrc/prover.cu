@@ -681,6 +681,35 @@ static void prove(Ctx* ctx, const Setup& st, const uint64_t* d_wit, uint64_t* pr
                 k += gate_relations(g.gates[gi].kind) * inst;
             }
             p.tail_term0 = k;
+            {   // work list of the gates kernel: cut into ZKGPU_QG_WARPS contiguous segments of equal estimated cost
+                // rough instruction counts per instance (ncu per-line counts of the MainVM / recursion / compression circuits)
+                static const uint32_t COST[ZKGPU_GATE_KINDS] = {0, 25, 60, 110, 45, 200, 80, 80, 110, 600, 0, 330, 60, 40, 1500, 1500, 120, 360, 80, 40};
+                const uint32_t PER_GATE = 250;   // selector product + alpha-dot reduction, paid by every warp that touches the gate
+                uint64_t total = 0;
+                for (uint32_t gi = 0; gi < g.n_gates; gi++) {
+                    const uint32_t inst = g.gates[gi].kind == ZKGPU_GATE_POSEIDON2_FLATTENED ? 0 : gate_instances(g.gates[gi], g);
+                    if (inst) total += PER_GATE + (uint64_t)inst * COST[g.gates[gi].kind];
+                }
+                uint64_t base = 0;
+                for (uint32_t gi = 0; gi < g.n_gates; gi++) {
+                    const uint32_t inst = g.gates[gi].kind == ZKGPU_GATE_POSEIDON2_FLATTENED ? 0 : gate_instances(g.gates[gi], g);
+                    const uint64_t c = COST[g.gates[gi].kind] ? COST[g.gates[gi].kind] : 1;
+                    uint32_t prev = 0;
+                    for (uint32_t q = 0; q < ZKGPU_QG_WARPS; q++) {
+                        // instances whose start cost lies below the upper cut of warp q
+                        const uint64_t hi = total * (q + 1) / ZKGPU_QG_WARPS;
+                        uint32_t end = inst;
+                        if (q + 1 < ZKGPU_QG_WARPS) {
+                            const uint64_t b0 = base + PER_GATE;
+                            end = hi <= b0 ? 0 : (uint32_t)std::min<uint64_t>(inst, (hi - b0 + c - 1) / c);
+                        }
+                        if (end < prev) end = prev;
+                        p.gate_t0[q][gi] = (uint16_t)prev; p.gate_t1[q][gi] = (uint16_t)end;
+                        prev = end;
+                    }
+                    if (inst) base += PER_GATE + (uint64_t)inst * c;
+                }
+            }
             ZK_REQUIRE(g.lookup_width < 9, "prove: lookup width too large");
             p.lgamma_pow[0] = gl::make2(1, 0);
             for (uint32_t q = 1; q < 9; q++) p.lgamma_pow[q] = gl::mul(p.lgamma_pow[q - 1], lgamma);

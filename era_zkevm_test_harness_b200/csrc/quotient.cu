@@ -40,11 +40,14 @@ __device__ __forceinline__ uint64_t selector(const uint64_t* __restrict__ kc, si
 // the constant columns are staged ONCE in shared memory -- one 256-byte TMA bulk copy (cp.async.bulk, 16-byte units) per column
 // onto an mbarrier -- and every gate kind reads them from there: the first version walked the columns in global memory once per
 // gate kind and pulled 6.2 GB per coset through HBM for 1.1 GB of columns (profiles/r01_m_summary.txt).  The QG_SPLIT warps of
-// the CTA take the instances t = warp, warp + QG_SPLIT, ... of every gate for the same 32 points; their partial alpha-weighted
-// sums are added at the end (exact field additions, so the split does not change a bit of the result).
-constexpr int QG_P = 32;   // 2 warps: measured 15.9 ms per proof against 17.6 ms with 4 (each warp repeats the selector and loop set-up)
+// the CTA share the (gate, instance) work list of the same 32 points: the host cuts the list into QG_SPLIT contiguous segments of
+// equal estimated cost (QuotParams::gate_t0 / gate_t1), so a gate is set up -- selector product, alpha-dot reduction -- by ONE warp
+// unless it straddles a cut; the partial alpha-weighted sums are added at the end (exact field additions: the split does not
+// change a bit of the result).  The first version strided every gate's instances over the warps, so each warp repeated the per-gate
+// set-up (14.95 ms per proof with 2 warps; the contiguous split: 14.1 ms with 2 warps, 14.8 with 3, 14.9 with 4).
+constexpr int QG_P = 32;
 #ifndef ZK_QG_SPLIT
-#define ZK_QG_SPLIT 2
+#define ZK_QG_SPLIT ZKGPU_QG_WARPS
 #endif
 constexpr int QG_SPLIT = ZK_QG_SPLIT;
 static size_t quotient_gates_smem(const zkgpu_geometry& g) {
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
 #pragma unroll 1
     for (uint32_t gi = 0; gi < p.g.n_gates; gi++) {
         const zkgpu_gate gt = p.g.gates[gi];
-        const uint32_t inst = gate_instances(gt, p.g);
-        if (!inst || gt.kind == ZKGPU_GATE_POSEIDON2_FLATTENED) continue;
+        const uint32_t tb = p.gate_t0[warp][gi], te = p.gate_t1[warp][gi];   // this warp's instances of the gate
+        if (tb >= te || gt.kind == ZKGPU_GATE_POSEIDON2_FLATTENED) continue;
         const uint64_t* __restrict__ gk = kc + (size_t)gt.path_len * cs;
         const ulonglong2* __restrict__ ap = apow + p.gate_term0[gi];
         DotE2 d;
@@ -114,12 +117,12 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
         switch (gt.kind) {
             case ZKGPU_GATE_CONSTANTS_ALLOCATOR:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) dote_add(d, gl::sub(w[(size_t)t * cw], gk[(size_t)t * cs]), ap[t]);
+                for (uint32_t t = tb; t < te; t++) dote_add(d, gl::sub(w[(size_t)t * cw], gk[(size_t)t * cs]), ap[t]);
                 break;
             case ZKGPU_GATE_FMA: {
                 const uint64_t k0 = gk[0], k1 = gk[cs];
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
                     uint64_t r = gl::sub(glx::fma(glx::mul(k0, x[0]), x[cw], glx::mul(k1, x[2 * cw])), x[3 * cw]);
                     dote_add(d, r, ap[t]);
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_REDUCTION4: {
                 const uint64_t k0 = gk[0], k1 = gk[cs], k2 = gk[2 * cs], k3 = gk[3 * cs];
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t s = glx::fma(k3, x[3 * cw], glx::fma(k2, x[2 * cw], glx::fma(k1, x[cw], glx::mul(k0, x[0]))));
                     dote_add(d, gl::sub(s, x[4 * cw]), ap[t]);
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             } break;
             case ZKGPU_GATE_SELECTION:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(4 * t) * cw;
                     uint64_t b = x[2 * cw];
                     // s*a + (1-s)*b - out = s*(a - b) + b - out
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                 break;
             case ZKGPU_GATE_PARALLEL_SELECTION4:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(13 * t) * cw;
                     const uint64_t s = x[0];
 #pragma unroll 1
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                 break;
             case ZKGPU_GATE_ZERO_CHECK:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(3 * t) * cw;
                     uint64_t xv = x[0], zf = x[2 * cw];
                     dote_add(d, gl::sub(glx::mul(xv, x[cw]), gl::sub(1, zf)), ap[2 * t]);
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_UINTX_ADD: {
                 const uint64_t k0 = gk[0];
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t co = x[4 * cw];
                     // a + b + cin - c - k*cout, as (a + b + cin) + (p - c) + k*(p - cout): every term canonical, sums lazy
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             } break;
             case ZKGPU_GATE_U32_TRI_ADD_CARRY:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(5 * t) * cw;
                     uint64_t lhs = gl::add(gl::add(x[0], x[cw]), x[2 * cw]);
                     dote_add(d, gl::sub(lhs, gl::add(x[3 * cw], gl::mul_pow2(x[4 * cw], 32))), ap[t]);
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_BOUNDED_BOOLEAN:
             case ZKGPU_GATE_BOOLEAN_ALL:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t x = w[(size_t)t * cw];
                     dote_add(d, gl::sub(gl::sqr(x), x), ap[t]);
                 }
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_MATMUL12_EXTERNAL:
             case ZKGPU_GATE_MATMUL12_INNER:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(24 * t) * cw;
                     uint64_t s[12];
 #pragma unroll
@@ -211,14 +214,14 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_NONLINEARITY7: {
                 const uint64_t k0 = gk[0];
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(2 * t) * cw;
                     dote_add(d, gl::sub(x[cw], glx::canon(glx::pow7(glx::add_canon(x[0], k0)))), ap[t]);
                 }
             } break;
             case ZKGPU_GATE_CONDITIONAL_SWAP4:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(17 * t) * cw;
                     const uint64_t sw = x[8 * cw];
 #pragma unroll 1
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_ZERO_CHECK_WITNESS: {
                 const uint64_t* pw = w + (size_t)n_copy * cw;   // plain witness cells follow the copy columns in the tile
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(2 * t) * cw;
                     uint64_t xv = x[0], zf = x[cw];
                     dote_add(d, gl::sub(gl::mul(xv, pw[(size_t)t * cw]), gl::sub(1, zf)), ap[2 * t]);
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             } break;
             case ZKGPU_GATE_DOT_PRODUCT4:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(9 * t) * cw;
                     uint64_t s = glx::fma(x[6 * cw], x[7 * cw], glx::fma(x[4 * cw], x[5 * cw], glx::fma(x[2 * cw], x[3 * cw], glx::mul(x[0], x[cw]))));
                     dote_add(d, gl::sub(s, x[8 * cw]), ap[t]);
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
                 break;
             case ZKGPU_GATE_U8X4_FMA:
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(26 * t) * cw;
                     // sum_{i,j} a_i b_j 2^(8(i+j)), grouped by i+j; then the linear part, byte position by byte position
                     uint64_t a[4], b[4];
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(32 * QG_SPLIT, 16 / QG_SPLIT) quotient_gates_k
             case ZKGPU_GATE_FMA_EXT: {
                 const gl::e2 k0 = gl::make2(gk[0], gk[cs]), k1 = gl::make2(gk[2 * cs], gk[3 * cs]);
 #pragma unroll 1
-                for (uint32_t t = warp; t < inst; t += QG_SPLIT) {
+                for (uint32_t t = tb; t < te; t++) {
                     const uint64_t* x = w + (size_t)(8 * t) * cw;
                     gl::e2 ab = gl::mul(gl::make2(x[0], x[cw]), gl::make2(x[2 * cw], x[3 * cw]));
                     gl::e2 r = gl::sub(gl::add(gl::mul(k0, ab), gl::mul(k1, gl::make2(x[4 * cw], x[5 * cw]))), gl::make2(x[6 * cw], x[7 * cw]));

@@ -4,6 +4,10 @@
 
 namespace zk {
 
+#ifndef ZKGPU_QG_WARPS
+#define ZKGPU_QG_WARPS 2   // warps per 32-point tile of quotient_gates_kernel (measured per proof: 2 warps 14.1 ms, 3: 14.8, 4: 14.9)
+#endif
+
 struct QuotParams {
     zkgpu_geometry g;
     const uint64_t* wit;    // coset evaluations, column stride cs_w, already offset to the coset
@@ -19,6 +23,8 @@ struct QuotParams {
     uint64_t* t1;              // output (split Ext2), offset to the coset
     uint32_t NP, C, E2, W, lookup_col0;
     uint32_t gate_term0[ZKGPU_MAX_GATES];  // index of the first alpha power of each gate
+    uint16_t gate_t0[ZKGPU_QG_WARPS][ZKGPU_MAX_GATES];   // quotient_gates_kernel: warp q evaluates instances [gate_t0[q][g], gate_t1[q][g])
+    uint16_t gate_t1[ZKGPU_QG_WARPS][ZKGPU_MAX_GATES];   // of gate g (contiguous cost-balanced segments of the work list)
     uint32_t p2_gate;                      // index of the flattened Poseidon2 gate in g.gates, 0xFFFFFFFF if absent
     uint32_t tail_term0;                   // first alpha power after the gate terms (boolean column, PI, lookup, copy permutation)
     uint64_t shift, xn_minus_1, zh_inv, n_field;
