@@ -50,6 +50,31 @@ GL_HD void p2x_internal(uint64_t (&s)[12]) {
     }
 }
 
+// Two partial rounds with ONE reduction of lanes 1..11: after the first round the lanes stay exact 96-bit integers
+// (2^sh * x + sum < 2^79), the second round shifts and sums those (< 2^94) and reduces.  Saves 11 reduce96 per pair of rounds.
+template <typename RC>
+GL_HD void p2x_partial_pair(uint64_t (&s)[12], const RC& rc, int r) {
+    constexpr unsigned SH[12] = {4, 14, 11, 8, 0, 5, 2, 9, 13, 6, 3, 12};
+    s[0] = glx::pow7(glx::add_canon(s[0], rc[12 * r]));
+    glx::w96 sum = glx::widen(s[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) sum = glx::add(sum, s[i]);
+    glx::w96 y[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        glx::w96 x = glx::widen(s[i]);
+        if (SH[i]) x = glx::shl(x, SH[i]);
+        y[i] = glx::add(x, sum);
+    }
+    const uint64_t y0 = glx::pow7(glx::add_canon(glx::reduce(y[0]), rc[12 * (r + 1)]));
+    glx::w96 sum2 = glx::widen(y0);
+#pragma unroll
+    for (int i = 1; i < 12; i++) sum2 = glx::add(sum2, y[i]);
+    s[0] = glx::reduce(glx::add(glx::shl(glx::widen(y0), SH[0]), sum2));
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = glx::reduce(glx::add(SH[i] ? glx::shl(y[i], SH[i]) : y[i], sum2));
+}
+
 // One full round on 4 lanes at a time with the state rotated by 4 between iterations, so the S-box code (4 x 4
 // multiplies) exists ONCE in the instruction stream and is executed 3 times per round: the whole permutation is ~12 KB of
 // SASS instead of ~45 KB fully unrolled.  The hash kernels are instruction-fetch-bound otherwise (ncu: stall_no_instruction
@@ -85,11 +110,16 @@ GL_HD void p2x_permute(uint64_t (&s)[12], const RC& rc) {
 #pragma unroll 1
         for (int k = 0; k < 4; k++, r++) p2x_full_round(s, rc, r);
         if (half == 0) {
+#ifndef ZK_P2_SINGLE_PARTIAL   // paired partial rounds: 1.575 -> 1.619 G permutations/s (tools/microbench/p2bench.cu)
+#pragma unroll 1
+            for (int k = 0; k < 11; k++, r += 2) p2x_partial_pair(s, rc, r);
+#else
 #pragma unroll 1
             for (int k = 0; k < 22; k++, r++) {
                 s[0] = glx::pow7(glx::add_canon(s[0], rc[12 * r]));
                 p2x_internal(s);
             }
+#endif
         }
     }
 }
