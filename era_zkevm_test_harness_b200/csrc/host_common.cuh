@@ -82,7 +82,7 @@ inline std::vector<uint64_t> copy_permutation_non_residues(uint32_t n, int log_n
 constexpr uint64_t PROOF_MAGIC = 0x5A4B50524F4F4631ULL;
 
 // boojum's AlgebraicSpongeBasedTranscript<F, 8, 12, 4, Poseidon2Goldilocks>, PINNED on the reference's golden proofs
-// (tools/golden_transcript.py, tests/test_golden_transcript_cpu.py: z, the DEEP challenge and every FRI challenge equal the values
+// (tools/golden_transcript.py, tests/test_golden_verify_cpu.py: z, the DEEP challenge and every FRI challenge equal the values
 // recovered hash-free, and every transcript-derived query index opens all Merkle paths of compression_1..4 and proof.json):
 // witnessed elements are buffered; a challenge request absorbs the buffer followed by a ONE (rate 8, overwrite, then zero fill,
 // one permutation per block; the state is never reset) and the 8 RATE lanes of the state become the list of available

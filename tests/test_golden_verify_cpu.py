@@ -72,3 +72,37 @@ def test_reference_proof_passes_the_quotient_identity():
     geo, cfg, cap, flat = load_pair(os.path.join(HERE, "golden", "pair_node_3.json"))
     ok, msg = oracle_lib.load().verify(geo, cfg, cap, flat)
     assert ok, msg
+
+
+DEEP_FOR_PAIR = {"compression_1": "deep_compression_1", "compression_2": "deep_compression_2", "node_3": "deep_node_3_0_0",
+                 "base_8": "deep_ram_8_0", "base_13": "deep_l1_messages_hasher_13_0"}
+FRI_FOR_PAIR = {"compression_1": "fri_chain_compression_1", "compression_2": "fri_chain_compression_2", "node_3": "fri_chain_node_3_0_0",
+                "base_8": "fri_chain_ram_8_0"}
+
+
+@pytest.mark.parametrize("pair", sorted(DEEP_FOR_PAIR))
+def test_transcript_challenges_equal_the_hash_free_recoveries(pair):
+    """Two independent routes to the same numbers: z, the DEEP challenge and the FRI fold challenges replayed through the pinned
+    Poseidon2 transcript (tools/golden_transcript.py) against the values tools/golden_deep.py / golden_fri_chain.py had recovered
+    from the same proofs algebraically, without any hash (tests/golden/deep_*.json, fri_chain_*.json)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from tools.golden_transcript import Transcript, flat_cap
+    d = json.load(open(os.path.join(HERE, "golden", f"pair_{pair}.json")))
+    vk, pr = d["vk"], d["proof"]
+    deep = json.load(open(os.path.join(HERE, "golden", DEEP_FOR_PAIR[pair] + ".json")))
+    tr = Transcript(n_chal=8)
+    tr.absorb(flat_cap(vk["setup_merkle_tree_cap"])); tr.absorb(pr["public_inputs"]); tr.absorb(flat_cap(pr["witness_oracle_cap"]))
+    for _ in range(8 if pr["values_at_0"] else 4): tr.challenge()             # beta, gamma (+ lookup beta, gamma)
+    tr.absorb(flat_cap(pr["stage_2_oracle_cap"])); tr.challenge(); tr.challenge()   # alpha
+    tr.absorb(flat_cap(pr["quotient_oracle_cap"]))
+    assert tr.challenge_ext() == deep["z"]
+    for key in ("values_at_z", "values_at_z_omega", "values_at_0"):
+        tr.absorb([x for e in pr[key] for x in e["coeffs"]])
+    assert tr.challenge_ext() == deep["phi"]
+    if pair in FRI_FOR_PAIR:
+        fri = json.load(open(os.path.join(HERE, "golden", FRI_FOR_PAIR[pair] + ".json")))
+        got = []
+        for cap in [pr["fri_base_oracle_cap"]] + pr["fri_intermediate_oracles_caps"]:
+            tr.absorb(flat_cap(cap)); got.append(tr.challenge_ext())
+        assert got == fri["challenges"]
