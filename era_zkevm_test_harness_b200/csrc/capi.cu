@@ -100,6 +100,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* ctx) {
         if (ctx->c.staged[k]) cudaFree(ctx->c.staged[k]);
         if (ctx->c.staged_ready[k]) cudaEventDestroy(ctx->c.staged_ready[k]);
         if (ctx->c.staged_free[k]) cudaEventDestroy(ctx->c.staged_free[k]);
+        for (int q = 0; q < 8; q++) if (ctx->c.staged_chunk[k][q]) cudaEventDestroy(ctx->c.staged_chunk[k][q]);
     }
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;

@@ -1064,7 +1064,19 @@ int zkgpu_witness_stage(zkgpu_ctx* ctx, const zkgpu_setup* s, const uint64_t* h_
             }
         }
         CUDA_CHECK(cudaStreamWaitEvent(c.copy_stream, c.staged_free[slot], 0));   // the proof that last read this slot is done
-        CUDA_CHECK(cudaMemcpyAsync(c.staged[slot], h_witness_cols, words * 8, cudaMemcpyHostToDevice, c.copy_stream));
+        {
+            const uint32_t W = s->s->sh.W;
+            const size_t N = s->s->sh.N;
+            const uint32_t chunk_cols = W >= 16 ? (W + 7) / 8 : W, n_chunks = (W + chunk_cols - 1) / chunk_cols;
+            for (uint32_t k = 0; k < n_chunks; k++) {
+                const uint32_t c0 = k * chunk_cols, c1 = c0 + chunk_cols < W ? c0 + chunk_cols : W;
+                CUDA_CHECK(cudaMemcpyAsync(c.staged[slot] + (size_t)c0 * N, h_witness_cols + (size_t)c0 * N, (size_t)(c1 - c0) * N * 8,
+                                           cudaMemcpyHostToDevice, c.copy_stream));
+                if (!c.staged_chunk[slot][k]) CUDA_CHECK(cudaEventCreateWithFlags(&c.staged_chunk[slot][k], cudaEventDisableTiming));
+                CUDA_CHECK(cudaEventRecord(c.staged_chunk[slot][k], c.copy_stream));
+            }
+            c.staged_chunk_cols[slot] = chunk_cols; c.staged_n_chunks[slot] = n_chunks;
+        }
         CUDA_CHECK(cudaEventRecord(c.staged_ready[slot], c.copy_stream));
         c.staged_valid[slot] = true;
         return 0;
@@ -1085,8 +1097,16 @@ int zkgpu_prove_staged(zkgpu_ctx* ctx, const zkgpu_setup* s, int slot, uint64_t*
         ZK_REQUIRE(c.staged_valid[slot] && c.staged_words[slot] >= (size_t)s->s->sh.W * s->s->sh.N, "prove_staged: no witness staged in this slot");
         c.staged_valid[slot] = false;
         CUDA_CHECK(cudaSetDevice(c.device));
-        CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.staged_ready[slot], 0));
-        zk::prove(&c, *s->s, c.staged[slot], h_proof_out, proof_capacity_u64);
+        if (cudaEventQuery(c.staged_ready[slot]) == cudaSuccess) {   // the witness has landed: one batched pass over all columns
+            CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.staged_ready[slot], 0));
+            zk::prove(&c, *s->s, c.staged[slot], h_proof_out, proof_capacity_u64);
+        } else {   // still crossing PCIe (first proof of a run): start on the column chunks as they land, like zkgpu_prove
+            (void)cudaGetLastError();   // cudaErrorNotReady from the query is not an error
+            zk::UploadPlan plan;
+            plan.chunk_cols = c.staged_chunk_cols[slot];
+            for (uint32_t k = 0; k < c.staged_n_chunks[slot]; k++) plan.ready.push_back(c.staged_chunk[slot][k]);
+            zk::prove(&c, *s->s, c.staged[slot], h_proof_out, proof_capacity_u64, &plan);
+        }
         CUDA_CHECK(cudaEventRecord(c.staged_free[slot], c.stream));
         CUDA_CHECK(cudaStreamSynchronize(c.stream));
         return 0;

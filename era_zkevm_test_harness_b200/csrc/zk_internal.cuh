@@ -70,6 +70,10 @@ struct Ctx {
     size_t staged_words[2] = {0, 0};
     bool staged_valid[2] = {false, false};
     cudaEvent_t staged_ready[2] = {nullptr, nullptr}, staged_free[2] = {nullptr, nullptr};
+    // the staged upload goes in up to 8 column chunks, each with its own event: a proof whose witness is still crossing PCIe starts on
+    // the chunks that have landed (first proof of a run); a fully landed witness is proven in one batch
+    cudaEvent_t staged_chunk[2][8] = {{nullptr}, {nullptr}};
+    uint32_t staged_chunk_cols[2] = {0, 0}, staged_n_chunks[2] = {0, 0};
 
     void* alloc_persistent(size_t bytes) {
         void* p = nullptr;
